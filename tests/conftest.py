@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    gdir = os.path.join(ROOT, "tests", "golden")
+
+    class G:
+        def __getattr__(self, name):
+            d = np.load(os.path.join(gdir, "golden_%s.npz" % name), allow_pickle=False)
+            setattr(self, name, d)
+            return d
+    return G()
