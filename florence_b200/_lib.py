@@ -1,0 +1,87 @@
+"""ctypes binding of libflorence_b200.so (the C ABI declared in include/florence_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or a call fails, the product path raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflorence_b200.so")
+
+FL_OK = 0
+FL_ERR_INVALID, FL_ERR_UNSUPPORTED, FL_ERR_CUDA, FL_ERR_STATE = -1, -2, -3, -4
+FL_MODE_COO, FL_MODE_CSR = 0, 1
+
+# every symbol include/florence_b200.h declares (checked by tests/test_cabi.py)
+EXPORTS = ["fl_last_error", "fl_version", "fl_create", "fl_destroy", "fl_assemble_explicit", "fl_pattern_build", "fl_pattern_export",
+           "fl_pattern_export_data_indices", "fl_assemble_implicit", "fl_assemble_laplacian", "fl_assemble_mass", "fl_explicit_steps",
+           "fl_pack_nodes", "fl_unpack_add_nodes", "fl_explicit_update", "fl_measure_fp64_peak"]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("nodeperelem", C.c_int32), ("ngauss", C.c_int32), ("reserved", C.c_int32),
+                ("nelem", C.c_int64), ("nnode", C.c_int64), ("points", C.c_void_p), ("elements", C.c_void_p),
+                ("bases", C.c_void_p), ("Jm", C.c_void_p), ("AllGauss", C.c_void_p)]
+
+
+class Material(C.Structure):
+    _fields_ = [("material_number", C.c_int32), ("reserved", C.c_int32), ("rho", C.c_double), ("mu", C.c_double), ("mu1", C.c_double),
+                ("mu2", C.c_double), ("mu3", C.c_double), ("mue", C.c_double), ("lamb", C.c_double), ("eps_1", C.c_double),
+                ("eps_2", C.c_double), ("eps_3", C.c_double), ("eps_e", C.c_double)]
+
+
+class ExplicitCtrl(C.Structure):
+    _fields_ = [("dt", C.c_double), ("fext_scale0", C.c_double), ("fext_scale_step", C.c_double), ("increment", C.c_int64),
+                ("nsteps", C.c_int64)]
+
+
+class FlorenceB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FlorenceB200Error("libflorence_b200.so is not built (run `python -m florence_b200.build`); "
+                                "there is no CPU fallback for the assembly hot path")
+    lib = C.CDLL(LIB_PATH)
+    lib.fl_last_error.restype = C.c_char_p
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    lib.fl_create.argtypes = [C.POINTER(MeshDesc), C.POINTER(vp)]
+    lib.fl_destroy.argtypes = [vp]
+    lib.fl_assemble_explicit.argtypes = [vp, vp, vp, C.POINTER(Material), i32, vp, vp]
+    lib.fl_pattern_build.argtypes = [vp, i32, C.POINTER(i64)]
+    lib.fl_pattern_export.argtypes = [vp, i32, vp, vp, vp]
+    lib.fl_pattern_export_data_indices.argtypes = [vp, i32, vp, vp, vp]
+    lib.fl_assemble_implicit.argtypes = [vp, vp, vp, C.POINTER(Material), i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.fl_assemble_laplacian.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.fl_assemble_mass.argtypes = [vp, dbl, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.fl_explicit_steps.argtypes = [vp, C.POINTER(Material), C.POINTER(ExplicitCtrl), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fl_pack_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
+    lib.fl_unpack_add_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
+    lib.fl_explicit_update.argtypes = [vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fl_measure_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl)]
+    for name in EXPORTS:
+        if name != "fl_last_error":
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Map a status code to the exception the reference raises in the same situation."""
+    if rc == FL_OK:
+        return
+    msg = load().fl_last_error().decode()
+    if rc == FL_ERR_UNSUPPORTED:
+        # _LowLevelAssembly_.py:58-60 and _LowLevelAssemblyExplicit_DF_DPF_.pyx:107-109 raise NotImplementedError
+        raise NotImplementedError(msg)
+    if rc == FL_ERR_INVALID:
+        raise ValueError(msg)
+    raise FlorenceB200Error("libflorence_b200 error %d: %s" % (rc, msg))

@@ -1,0 +1,236 @@
+"""Device-side assembly handle: torch tensors in, torch tensors out, all work done by libflorence_b200.so.
+
+torch is plumbing only (device memory, streams, DLPack exchange); every number is produced by the CUDA kernels behind the C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ExplicitCtrl, Material, MeshDesc, check
+
+# Florence/FiniteElements/Assembly/_Assembly_/_LowLevelAssemblyExplicit_DF_DPF_.pyx:72-109
+MATERIAL_NUMBERS = {
+    "ExplicitMooneyRivlin": 0,
+    "NeoHookean": 1,
+    "MooneyRivlin": 2,
+    "NearlyIncompressibleMooneyRivlin": 3,
+    "IsotropicElectroMechanics_101": 4,
+    "IsotropicElectroMechanics_105": 5,
+    "IsotropicElectroMechanics_106": 6,
+    "IsotropicElectroMechanics_107": 7,
+    "IsotropicElectroMechanics_108": 8,
+    "ExplicitIsotropicElectroMechanics_108": 9,
+    "LinearElastic": 10,
+    "IncrementalLinearElastic": 10,
+}
+ELECTRO_NUMBERS = (4, 5, 6, 7, 8, 9)
+
+
+def to_device(x, dtype, device):
+    """numpy array / torch tensor / any DLPack exporter (cupy, jax, ...) -> contiguous torch tensor on `device`."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        if x.dtype == np.uint64:
+            # torch's uint64 support is partial; the bit pattern is what the C ABI reads
+            x = x.view(np.int64)
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        t = torch.as_tensor(np.asarray(x))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+def make_material(material_number, rho=0.0, **constants):
+    m = Material()
+    m.material_number = int(material_number)
+    m.rho = float(rho if rho is not None else 0.0)
+    for k, v in constants.items():
+        setattr(m, k, float(v))
+    return m
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class AssemblyHandle(object):
+    """Caches a mesh + function-space tables on the device (fl_create) and exposes the assembly entry points."""
+
+    def __init__(self, points, elements, Jm, AllGauss, Bases=None, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.FlorenceB200Error("florence_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            pts = to_device(points, torch.float64, self.device)
+            els = to_device(elements, torch.int64, self.device)
+            jm = to_device(Jm, torch.float64, self.device)
+            gw = to_device(AllGauss, torch.float64, self.device).reshape(-1)
+            bs = None if Bases is None else to_device(Bases, torch.float64, self.device)
+            self.nnode, self.ndim = int(pts.shape[0]), int(pts.shape[1])
+            self.nelem, self.npe = int(els.shape[0]), int(els.shape[1])
+            self.ngauss = int(gw.shape[0])
+            if tuple(jm.shape) != (self.ndim, self.npe, self.ngauss):
+                raise ValueError("Jm must be (ndim x nodeperelem x ngauss), got %s" % (tuple(jm.shape),))
+            desc = MeshDesc(self.ndim, self.npe, self.ngauss, 0, self.nelem, self.nnode, pts.data_ptr(), els.data_ptr(),
+                            0 if bs is None else bs.data_ptr(), jm.data_ptr(), gw.data_ptr())
+            h = C.c_void_p()
+            torch.cuda.synchronize(self.device)
+            check(self.lib.fl_create(C.byref(desc), C.byref(h)))
+            self._h = h
+        self._pattern_nvar = {}
+        self.nnz = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.fl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------------- explicit
+    def assemble_explicit(self, Eulerx, Eulerp, material, formulation_number=0, out=None):
+        nvar = self.ndim + (1 if formulation_number == 1 else 0)
+        x = to_device(Eulerx, torch.float64, self.device)
+        p = None if Eulerp is None else to_device(Eulerp, torch.float64, self.device).reshape(-1)
+        T = out if out is not None else torch.empty(self.nnode * nvar, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_assemble_explicit(self._h, _ptr(x), _ptr(p), C.byref(material), formulation_number, _ptr(T), _stream()))
+        return T
+
+    # ---------------------------------------------------------------------------------------------- pattern
+    def build_pattern(self, nvar):
+        if nvar not in self.nnz:
+            nnz = C.c_int64(0)
+            with torch.cuda.device(self.device):
+                check(self.lib.fl_pattern_build(self._h, nvar, C.byref(nnz)))
+            self.nnz[nvar] = int(nnz.value)
+        return self.nnz[nvar]
+
+    def sparsity_pattern(self, nvar, with_data_indices=False):
+        """(indices, indptr[, data_local_indices, data_global_indices]) int32 device tensors, reference ordering."""
+        nnz = self.build_pattern(nvar)
+        if nvar not in self._pattern_nvar:
+            indptr = torch.empty(self.nnode * nvar + 1, dtype=torch.int32, device=self.device)
+            indices = torch.empty(nnz, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(self.lib.fl_pattern_export(self._h, nvar, _ptr(indptr), _ptr(indices), _stream()))
+            self._pattern_nvar[nvar] = (indices, indptr)
+        indices, indptr = self._pattern_nvar[nvar]
+        if not with_data_indices:
+            return indices, indptr
+        cap = (self.npe * nvar) ** 2
+        dl = torch.empty(cap * self.nelem, dtype=torch.int32, device=self.device)
+        dg = torch.empty(cap * self.nelem, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_pattern_export_data_indices(self._h, nvar, _ptr(dl), _ptr(dg), _stream()))
+        return indices, indptr, dl, dg
+
+    # ---------------------------------------------------------------------------------------------- implicit
+    def assemble_implicit(self, Eulerx, Eulerp, material, formulation_number=0, requires_geometry_update=True, mode="csr",
+                          out=None, with_indices=True):
+        """mode "coo": (I, J, V, T);  mode "csr": (V, T) aligned with sparsity_pattern(nvar)."""
+        nvar = self.ndim + (1 if formulation_number == 1 else 0)
+        ndof = self.npe * nvar
+        x = to_device(Eulerx, torch.float64, self.device)
+        p = None if Eulerp is None else to_device(Eulerp, torch.float64, self.device).reshape(-1)
+        I = J = None
+        if mode == "coo":
+            n = ndof * ndof * self.nelem
+            if out is not None:
+                I, J, V, T = out
+            else:
+                if with_indices:
+                    I = torch.empty(n, dtype=torch.int32, device=self.device)
+                    J = torch.empty(n, dtype=torch.int32, device=self.device)
+                V = torch.empty(n, dtype=torch.float64, device=self.device)
+                T = torch.empty(self.nnode * nvar, dtype=torch.float64, device=self.device)
+            imode = _lib.FL_MODE_COO
+        else:
+            nnz = self.build_pattern(nvar)
+            if out is not None:
+                V, T = out
+            else:
+                V = torch.empty(nnz, dtype=torch.float64, device=self.device)
+                T = torch.empty(self.nnode * nvar, dtype=torch.float64, device=self.device)
+            imode = _lib.FL_MODE_CSR
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_assemble_implicit(self._h, _ptr(x), _ptr(p), C.byref(material), formulation_number,
+                                                1 if requires_geometry_update else 0, imode, _ptr(I), _ptr(J), _ptr(V), _ptr(T), _stream()))
+        return (I, J, V, T) if mode == "coo" else (V, T)
+
+    def assemble_laplacian(self, e_tensor, is_hessian_symmetric=True, mode="csr"):
+        e = np.ascontiguousarray(np.asarray(e_tensor, dtype=np.float64))
+        if e.shape != (self.ndim, self.ndim):
+            raise ValueError("Permittivity tensor has to have a size of (ndim x ndim)")
+        I = J = None
+        if mode == "coo":
+            n = self.npe * self.npe * self.nelem
+            I = torch.empty(n, dtype=torch.int32, device=self.device)
+            J = torch.empty(n, dtype=torch.int32, device=self.device)
+            V = torch.empty(n, dtype=torch.float64, device=self.device)
+            imode = _lib.FL_MODE_COO
+        else:
+            V = torch.empty(self.build_pattern(1), dtype=torch.float64, device=self.device)
+            imode = _lib.FL_MODE_CSR
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_assemble_laplacian(self._h, e.ctypes.data_as(C.c_void_p), 1 if is_hessian_symmetric else 0, imode,
+                                                 _ptr(I), _ptr(J), _ptr(V), _stream()))
+            torch.cuda.current_stream().synchronize()  # e_tensor is read from host memory asynchronously
+        return (I, J, V) if mode == "coo" else V
+
+    def assemble_mass(self, rho, nvar, mass_type="lumped", mode="coo"):
+        if mass_type == "lumped":
+            M = torch.empty(self.nnode * nvar, dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                check(self.lib.fl_assemble_mass(self._h, float(rho), nvar, 0, 0, _ptr(M), None, None, None, _stream()))
+            return M
+        ndof = self.npe * nvar
+        I = J = None
+        if mode == "coo":
+            n = ndof * ndof * self.nelem
+            I = torch.empty(n, dtype=torch.int32, device=self.device)
+            J = torch.empty(n, dtype=torch.int32, device=self.device)
+            V = torch.empty(n, dtype=torch.float64, device=self.device)
+            imode = _lib.FL_MODE_COO
+        else:
+            V = torch.empty(self.build_pattern(nvar), dtype=torch.float64, device=self.device)
+            imode = _lib.FL_MODE_CSR
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_assemble_mass(self._h, float(rho), nvar, 1, imode, None, _ptr(I), _ptr(J), _ptr(V), _stream()))
+        return (I, J, V) if mode == "coo" else V
+
+    # ---------------------------------------------------------------------------------------------- explicit time loop
+    def explicit_steps(self, material, dt, nsteps, increment, M, fext, fixed_mask, inc_dirichlet, U0, U00, Eulerx, T,
+                       fext_scale0=0.0, fext_scale_step=0.0):
+        ctrl = ExplicitCtrl(float(dt), float(fext_scale0), float(fext_scale_step), int(increment), int(nsteps))
+        status = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_explicit_steps(self._h, C.byref(material), C.byref(ctrl), _ptr(M), _ptr(fext), _ptr(fixed_mask),
+                                             _ptr(inc_dirichlet), _ptr(U0), _ptr(U00), _ptr(Eulerx), _ptr(T), C.byref(status), _stream()))
+        return int(status.value)
+
+    def explicit_update(self, dt, fext_scale, M, fext, fixed_mask, inc_dirichlet, T, U0, U00, Eulerx, nan_flag=None):
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_explicit_update(self._h, float(dt), float(fext_scale), _ptr(M), _ptr(fext), _ptr(fixed_mask),
+                                              _ptr(inc_dirichlet), _ptr(T), _ptr(U0), _ptr(U00), _ptr(Eulerx), _ptr(nan_flag), _stream()))
+
+
+def measure_fp64_peak(use_dmma=False, iters=20000):
+    out = C.c_double(0.0)
+    check(_lib.load().fl_measure_fp64_peak(1 if use_dmma else 0, iters, C.byref(out)))
+    return out.value

@@ -1,0 +1,358 @@
+// fl_api.cu -- the C ABI of libflorence_b200.so (include/florence_b200.h): handle management, argument checks and the
+// sequencing of kernels for each reference entry point.
+#include <cstdarg>
+#include <cstring>
+
+#include "fl_internal.cuh"
+
+namespace fl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ensure_scratch(double** p, size_t* have, size_t need) {
+    if (*have >= need && *p) return FL_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    if (need == 0) need = 8;
+    FL_CUDA_CHECK(cudaMalloc(p, need));
+    *have = need;
+    return FL_OK;
+}
+
+__global__ void narrow_conn_kernel(const uint64_t* __restrict__ in, int64_t n, int64_t nnode, int32_t* __restrict__ out, int* __restrict__ bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t v = in[i];
+    if (v >= (uint64_t)nnode) *bad = 1;
+    out[i] = (int32_t)v;
+}
+
+__global__ void pad_jm_kernel(const double* __restrict__ in, int rows, int ng, int ldg, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ldg) return;
+    const int r = i / ldg, g = i - r * ldg;
+    out[i] = g < ng ? in[r * ng + g] : 0.0;
+}
+
+// ---- fp64 pipe peak micro-benchmarks -------------------------------------------------------------------
+__global__ void dfma_peak_kernel(int iters, double* out) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double b = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], b, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void dmma_peak_kernel(int iters, double* out) {
+    // mma.sync.aligned.m8n8k4.row.col.f64: 8x8x4 = 256 FMAs per warp instruction
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
+}  // namespace fl
+
+using namespace fl;
+
+extern "C" {
+
+const char* fl_last_error(void) { return g_err; }
+int fl_version(void) { return 100; }
+
+int fl_create(const fl_mesh_desc* m, fl_handle** out) {
+    if (!m || !out) { set_error("null argument"); return FL_ERR_INVALID; }
+    if (m->ndim != 2 && m->ndim != 3) { set_error("ndim must be 2 or 3, got %d", m->ndim); return FL_ERR_INVALID; }
+    if (m->nodeperelem < 1 || m->ngauss < 1 || m->nelem < 0 || m->nnode < 1) {
+        set_error("bad sizes: nodeperelem=%d ngauss=%d nelem=%lld nnode=%lld", m->nodeperelem, m->ngauss, (long long)m->nelem, (long long)m->nnode);
+        return FL_ERR_INVALID;
+    }
+    if (m->nnode >= (int64_t)1 << 31) { set_error("nnode exceeds int32 indexing"); return FL_ERR_INVALID; }
+    if (!m->points || !m->Jm || !m->AllGauss || (m->nelem > 0 && !m->elements)) { set_error("null mesh/table pointer"); return FL_ERR_INVALID; }
+    fl_handle* h = new fl_handle();
+    h->ndim = m->ndim; h->npe = m->nodeperelem; h->ng = m->ngauss; h->nelem = m->nelem; h->nnode = m->nnode;
+    h->ldg = m->ngauss | 1;
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(ce)); delete h; return FL_ERR_CUDA; }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int64_t nk = h->nelem * h->npe;
+    int rc = FL_OK;
+    auto fail = [&](int code) { fl_destroy(h); return code; };
+#define FL_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                            \
+            return fail(FL_ERR_CUDA);                                                             \
+        }                                                                                         \
+    } while (0)
+    FL_TRY(cudaMalloc(&h->conn, sizeof(int32_t) * (nk > 0 ? nk : 1)));
+    FL_TRY(cudaMalloc(&h->points, sizeof(double) * h->nnode * h->ndim));
+    FL_TRY(cudaMalloc(&h->jm, sizeof(double) * h->ndim * h->npe * h->ldg));
+    FL_TRY(cudaMalloc(&h->bases, sizeof(double) * h->npe * h->ng));
+    FL_TRY(cudaMalloc(&h->gw, sizeof(double) * h->ng));
+    FL_TRY(cudaMalloc(&h->flag, sizeof(int32_t)));
+    FL_TRY(cudaMemset(h->flag, 0, sizeof(int32_t)));
+    FL_TRY(cudaMemcpy(h->points, m->points, sizeof(double) * h->nnode * h->ndim, cudaMemcpyDeviceToDevice));
+    FL_TRY(cudaMemcpy(h->gw, m->AllGauss, sizeof(double) * h->ng, cudaMemcpyDeviceToDevice));
+    if (m->bases) FL_TRY(cudaMemcpy(h->bases, m->bases, sizeof(double) * h->npe * h->ng, cudaMemcpyDeviceToDevice));
+    else FL_TRY(cudaMemset(h->bases, 0, sizeof(double) * h->npe * h->ng));
+    {
+        const int tot = h->ndim * h->npe * h->ldg;
+        pad_jm_kernel<<<(tot + 255) / 256, 256>>>(m->Jm, h->ndim * h->npe, h->ng, h->ldg, h->jm);
+    }
+    if (nk > 0) {
+        narrow_conn_kernel<<<(unsigned)((nk + 255) / 256), 256>>>(m->elements, nk, h->nnode, h->conn, h->flag);
+        int bad = 0;
+        FL_TRY(cudaMemcpy(&bad, h->flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) { set_error("mesh.elements holds a node number >= nnode"); return fail(FL_ERR_INVALID); }
+    }
+    FL_TRY(cudaGetLastError());
+    rc = build_adjacency(h);
+    if (rc) return fail(rc);
+    FL_TRY(cudaDeviceSynchronize());
+#undef FL_TRY
+    *out = h;
+    return FL_OK;
+}
+
+int fl_destroy(fl_handle* h) {
+    if (!h) return FL_OK;
+    cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->bases); cudaFree(h->gw);
+    cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank);
+    cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag);
+    delete h;
+    return FL_OK;
+}
+
+int fl_assemble_explicit(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation_number,
+                         double* T, void* stream) {
+    if (!h || !Eulerx || !mat || !T) { set_error("null argument"); return FL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nvar = h->ndim + (formulation_number == 1 ? 1 : 0);
+    int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * h->npe * nvar);
+    if (rc) return rc;
+    rc = launch_explicit_elements(h, Eulerx, Eulerp, mat, formulation_number, h->te, st);
+    if (rc) return rc;
+    return launch_gather_nodes(h, nvar, h->te, T, st);
+}
+
+int fl_pattern_build(fl_handle* h, int nvar, int64_t* nnz_host) {
+    if (!h || nvar < 1 || nvar > 4) { set_error("bad argument"); return FL_ERR_INVALID; }
+    int rc = pattern_build(h);
+    if (rc) return rc;
+    if (nnz_host) *nnz_host = h->pat.nnzb * nvar * nvar;
+    return FL_OK;
+}
+
+int fl_pattern_export(fl_handle* h, int nvar, int32_t* indptr, int32_t* indices, void* stream) {
+    if (!h || !indptr || !indices) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_pattern_export(h, nvar, indptr, indices, (cudaStream_t)stream);
+}
+
+int fl_pattern_export_data_indices(fl_handle* h, int nvar, int32_t* dl, int32_t* dg, void* stream) {
+    if (!h || !dl || !dg) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_data_indices(h, nvar, dl, dg, (cudaStream_t)stream);
+}
+
+static int scatter_stiffness(fl_handle* h, int nvar, int mode, double* ke, int32_t* I, int32_t* J, double* V, cudaStream_t st) {
+    if (mode == FL_MODE_COO) {
+        if (I && J) return launch_coo_indices(h, nvar, I, J, st);
+        return FL_OK;
+    }
+    return launch_csr_gather(h, nvar, ke, V, st);
+}
+
+int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation_number,
+                         int requires_geometry_update, int mode, int32_t* I, int32_t* J, double* V, double* T, void* stream) {
+    if (!h || !Eulerx || !mat || !V || !T) { set_error("null argument"); return FL_ERR_INVALID; }
+    if (mode != FL_MODE_COO && mode != FL_MODE_CSR) { set_error("mode must be FL_MODE_COO or FL_MODE_CSR"); return FL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nvar = h->ndim + (formulation_number == 1 ? 1 : 0);
+    const size_t ndof = (size_t)h->npe * nvar;
+    if (mode == FL_MODE_CSR && !h->pat.nbr_ptr) { set_error("CSR assembly requires fl_pattern_build first"); return FL_ERR_STATE; }
+    int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * ndof);
+    if (rc) return rc;
+    double* ke = V;  // COO mode: the element kernel writes the triplet values in place
+    if (mode == FL_MODE_CSR) {
+        rc = ensure_scratch(&h->ke, &h->ke_bytes, sizeof(double) * h->nelem * ndof * ndof);
+        if (rc) return rc;
+        ke = h->ke;
+    }
+    rc = launch_implicit_elements(h, Eulerx, Eulerp, mat, formulation_number, requires_geometry_update ? 1 : 0, ke, h->te, st);
+    if (rc) return rc;
+    rc = scatter_stiffness(h, nvar, mode, ke, I, J, V, st);
+    if (rc) return rc;
+    return launch_gather_nodes(h, nvar, h->te, T, st);
+}
+
+int fl_assemble_laplacian(fl_handle* h, const double* e_tensor_host, int is_hessian_symmetric, int mode, int32_t* I, int32_t* J, double* V,
+                          void* stream) {
+    if (!h || !e_tensor_host || !V) { set_error("null argument"); return FL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == FL_MODE_CSR && !h->pat.nbr_ptr) { set_error("CSR assembly requires fl_pattern_build first"); return FL_ERR_STATE; }
+    // the d x d tensor rides in the traction scratch buffer
+    int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * 16);
+    if (rc) return rc;
+    FL_CUDA_CHECK(cudaMemcpyAsync(h->te, e_tensor_host, sizeof(double) * h->ndim * h->ndim, cudaMemcpyHostToDevice, st));
+    double* ke = V;
+    if (mode == FL_MODE_CSR) {
+        rc = ensure_scratch(&h->ke, &h->ke_bytes, sizeof(double) * h->nelem * h->npe * h->npe);
+        if (rc) return rc;
+        ke = h->ke;
+    }
+    rc = launch_laplacian_elements(h, h->te, is_hessian_symmetric ? 1 : 0, ke, st);
+    if (rc) return rc;
+    return scatter_stiffness(h, 1, mode, ke, I, J, V, st);
+}
+
+int fl_assemble_mass(fl_handle* h, double rho, int nvar, int mass_type, int mode, double* mass, int32_t* I, int32_t* J, double* V,
+                     void* stream) {
+    if (!h || nvar < 1 || nvar > 4) { set_error("bad argument"); return FL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ndof = (size_t)h->npe * nvar;
+    if (mass_type == 0) {
+        if (!mass) { set_error("null mass"); return FL_ERR_INVALID; }
+        int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * ndof);
+        if (rc) return rc;
+        rc = launch_mass_elements(h, rho, nvar, 1, h->te, st);
+        if (rc) return rc;
+        return launch_gather_nodes(h, nvar, h->te, mass, st);
+    }
+    if (!V) { set_error("null V"); return FL_ERR_INVALID; }
+    if (mode == FL_MODE_CSR && !h->pat.nbr_ptr) { set_error("CSR assembly requires fl_pattern_build first"); return FL_ERR_STATE; }
+    double* ke = V;
+    if (mode == FL_MODE_CSR) {
+        int rc = ensure_scratch(&h->ke, &h->ke_bytes, sizeof(double) * h->nelem * ndof * ndof);
+        if (rc) return rc;
+        ke = h->ke;
+    }
+    int rc = launch_mass_elements(h, rho, nvar, 0, ke, st);
+    if (rc) return rc;
+    return scatter_stiffness(h, nvar, mode, ke, I, J, V, st);
+}
+
+int fl_explicit_update(fl_handle* h, double dt, double fext_scale, const double* M, const double* fext, const uint8_t* fixed_mask,
+                       const double* inc_dirichlet, const double* T, double* U0, double* U00, double* Eulerx, int32_t* nan_flag_dev,
+                       void* stream) {
+    if (!h || !M || !T || !U0 || !U00 || !Eulerx) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_explicit_update(h, 0, nullptr, dt, fext_scale, M, fext, fixed_mask, inc_dirichlet, const_cast<double*>(T), U0, U00, Eulerx,
+                                  nan_flag_dev ? nan_flag_dev : h->flag, (cudaStream_t)stream);
+}
+
+int fl_explicit_steps(fl_handle* h, const fl_material* mat, const fl_explicit_ctrl* c, const double* M, const double* fext,
+                      const uint8_t* fixed_mask, const double* inc_dirichlet, double* U0, double* U00, double* Eulerx, double* T,
+                      int32_t* status_host, void* stream) {
+    if (!h || !mat || !c || !M || !U0 || !U00 || !Eulerx || !T) { set_error("null argument"); return FL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nvar = h->ndim;
+    int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * h->npe * nvar);
+    if (rc) return rc;
+    FL_CUDA_CHECK(cudaMemsetAsync(h->flag, 0, sizeof(int32_t), st));
+    for (int64_t s = 0; s < c->nsteps; ++s) {
+        const double fs = c->fext_scale0 + (double)(c->increment + s) * c->fext_scale_step;
+        // first step consumes the caller's T; later steps reduce the per-element tractions and update in one kernel
+        rc = launch_explicit_update(h, s == 0 ? 0 : 1, h->te, c->dt, fs, M, fext, fixed_mask, inc_dirichlet, T, U0, U00, Eulerx, h->flag, st);
+        if (rc) return rc;
+        rc = launch_explicit_elements(h, Eulerx, nullptr, mat, 0, h->te, st);
+        if (rc) return rc;
+    }
+    if (c->nsteps > 0) {
+        rc = launch_gather_nodes(h, nvar, h->te, T, st);
+        if (rc) return rc;
+    }
+    if (status_host) {
+        FL_CUDA_CHECK(cudaMemcpyAsync(status_host, h->flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FL_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return FL_OK;
+}
+
+__global__ void pack_nodes_kernel(const double* __restrict__ T, const int32_t* __restrict__ ids, int64_t n, int nvar, double* __restrict__ buf) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n * nvar) return;
+    const int64_t k = i / nvar;
+    buf[i] = T[(int64_t)ids[k] * nvar + (i - k * nvar)];
+}
+__global__ void unpack_add_nodes_kernel(double* __restrict__ T, const int32_t* __restrict__ ids, int64_t n, int nvar,
+                                        const double* __restrict__ buf) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n * nvar) return;
+    const int64_t k = i / nvar;
+    T[(int64_t)ids[k] * nvar + (i - k * nvar)] += buf[i];
+}
+
+int fl_pack_nodes(const double* T, const int32_t* node_ids, int64_t n, int nvar, double* buf, void* stream) {
+    if (n == 0) return FL_OK;
+    if (!T || !node_ids || !buf) { set_error("null argument"); return FL_ERR_INVALID; }
+    pack_nodes_kernel<<<(unsigned)((n * nvar + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, node_ids, n, nvar, buf);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+int fl_unpack_add_nodes(double* T, const int32_t* node_ids, int64_t n, int nvar, const double* buf, void* stream) {
+    if (n == 0) return FL_OK;
+    if (!T || !node_ids || !buf) { set_error("null argument"); return FL_ERR_INVALID; }
+    unpack_add_nodes_kernel<<<(unsigned)((n * nvar + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, node_ids, n, nvar, buf);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+int fl_measure_fp64_peak(int use_dmma, int iters, double* tflops_host) {
+    if (!tflops_host || iters < 1) { set_error("bad argument"); return FL_ERR_INVALID; }
+    int dev = 0, sms = 0;
+    FL_CUDA_CHECK(cudaGetDevice(&dev));
+    FL_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    FL_CUDA_CHECK(cudaMalloc(&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    FL_CUDA_CHECK(cudaEventCreate(&e0));
+    FL_CUDA_CHECK(cudaEventCreate(&e1));
+    const int threads = 256, blocks = sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        FL_CUDA_CHECK(cudaEventRecord(e0));
+        if (use_dmma) dmma_peak_kernel<<<blocks, threads>>>(iters, out);
+        else dfma_peak_kernel<<<blocks, threads>>>(iters, out);
+        FL_CUDA_CHECK(cudaEventRecord(e1));
+        FL_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        FL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = use_dmma ? (double)blocks * (threads / 32) * iters * 8.0 * 512.0 : (double)blocks * threads * iters * 16.0 * 2.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops_host = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    return FL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// fl_internal.cuh -- handle layout and launcher declarations shared by the translation units of libflorence_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/florence_b200.h"
+#include "fl_math.cuh"
+
+namespace fl {
+
+void set_error(const char* fmt, ...);
+
+#define FL_CUDA_CHECK(expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            fl::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return FL_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+// Node-level sparsity pattern (a14): row-node n has neighbour nodes nbr_idx[nbr_ptr[n] .. nbr_ptr[n+1]) ascending.
+// The CSR pattern of the (nvar*nnode)^2 matrix follows as indptr[nvar*n+i] = nvar*(nvar*nbr_ptr[n] + i*cnt_n),
+// indices = nvar*m+l.  rank[(e*npe+a)*npe+b] = position of node conn[e][b] in the neighbour list of conn[e][a].
+struct Pattern {
+    int64_t nnzb = 0;          // number of node pairs
+    int64_t* nbr_ptr = nullptr;  // nnode+1
+    int32_t* nbr_idx = nullptr;  // nnzb
+    uint16_t* rank = nullptr;    // nelem*npe*npe
+    int max_cnt = 0;           // widest row in nodes
+};
+
+}  // namespace fl
+
+struct fl_handle {
+    int ndim = 0, npe = 0, ng = 0;
+    int64_t nelem = 0, nnode = 0;
+    int ldg = 0;                 // padded (odd) leading dimension of the Jm table over gauss points
+    // device copies
+    int32_t* conn = nullptr;     // nelem x npe
+    double* points = nullptr;    // nnode x ndim
+    double* jm = nullptr;        // [k][a][ldg]: Jm[k][a][g]
+    double* bases = nullptr;     // [a][ng]
+    double* gw = nullptr;        // [ng]
+    // node -> flat connectivity index (e*npe+a), ascending in e: the order the reference's element loop sums in
+    int64_t* adj_ptr = nullptr;  // nnode+1
+    int32_t* adj_idx = nullptr;  // nelem*npe
+    int max_adj = 0;
+    fl::Pattern pat;
+    // scratch (grown on demand)
+    double* te = nullptr;  size_t te_bytes = 0;   // per-element traction buffer nelem*ndof
+    double* ke = nullptr;  size_t ke_bytes = 0;   // per-element stiffness buffer nelem*ndof^2 (CSR mode)
+    int32_t* flag = nullptr;                       // device status word
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+namespace fl {
+
+int ensure_scratch(double** p, size_t* have, size_t need);
+
+// fl_explicit.cu
+int launch_explicit_elements(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation,
+                             double* te, cudaStream_t st);
+int launch_gather_nodes(fl_handle* h, int nvar, const double* te, double* T, cudaStream_t st);
+int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, double dt, double fext_scale, const double* M,
+                           const double* fext, const uint8_t* fixed, const double* inc_dir, double* T, double* U0, double* U00,
+                           double* Eulerx, int32_t* nan_flag, cudaStream_t st);
+// fl_implicit.cu
+int launch_implicit_elements(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation,
+                             int update, double* ke, double* te, cudaStream_t st);
+int launch_laplacian_elements(fl_handle* h, const double* e_tensor, int symmetric, double* ke, cudaStream_t st);
+int launch_mass_elements(fl_handle* h, double rho, int nvar, int lumped, double* out, cudaStream_t st);
+// fl_pattern.cu
+int build_adjacency(fl_handle* h);
+int pattern_build(fl_handle* h);
+int launch_pattern_export(fl_handle* h, int nvar, int32_t* indptr, int32_t* indices, cudaStream_t st);
+int launch_data_indices(fl_handle* h, int nvar, int32_t* dl, int32_t* dg, cudaStream_t st);
+int launch_coo_indices(fl_handle* h, int nvar, int32_t* I, int32_t* J, cudaStream_t st);
+int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st);
+
+}  // namespace fl

@@ -1,0 +1,262 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden fixtures.
+
+Tolerances (fp64, BASELINE.json north_star): stiffness entries |dK| <= 1e-10 * max|K| (per block for electro-mechanics, whose
+blocks live on scales 20 orders of magnitude apart), residual ||dT|| <= 1e-11 ||T||; sparsity pattern and slot maps bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ELEC = ["IsotropicElectroMechanics_101", "IsotropicElectroMechanics_105", "IsotropicElectroMechanics_108"]
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cases():
+    d = np.load(os.path.join(GOLD, "golden_assembly.npz"))
+    return [str(s) for s in d["asm_cases"]]
+
+
+def _load(key):
+    g = np.load(os.path.join(GOLD, "golden_assembly.npz"))
+    names = ("points", "elements", "Eulerx", "Jm", "AllGauss", "Bases", "K_data", "K_indices", "K_indptr", "T", "update", "prm",
+             "sp_indices", "sp_indptr")
+    c = {n: g[key + "_" + n] for n in names}
+    c["Eulerp"] = g[key + "_Eulerp"] if key + "_Eulerp" in g.files else None
+    c["sp_dl"] = g[key + "_sp_dl"] if key + "_sp_dl" in g.files else None
+    c["sp_dg"] = g[key + "_sp_dg"] if key + "_sp_dg" in g.files else None
+    if int(c["update"]) == 0:
+        c["Eulerx"] = c["points"]
+    return c
+
+
+def _material(backend, num, prm):
+    return backend.make_material(num, 0.0, mu=prm[0], mu1=prm[1], mu2=prm[2], mu3=prm[3], mue=prm[4], lamb=prm[5], eps_1=prm[6],
+                                 eps_2=prm[7], eps_3=prm[8], eps_e=prm[9])
+
+
+def _blockwise_close(K, Kref, nvar, ndim, tol):
+    n = K.shape[0]
+    if nvar == ndim:
+        assert abs(K - Kref).max() <= tol * abs(Kref).max()
+        return
+    mech = np.arange(n) % nvar != ndim
+    for ra in (mech, ~mech):
+        for ca in (mech, ~mech):
+            A, B = K[ra][:, ca], Kref[ra][:, ca]
+            assert abs(A - B).max() <= tol * abs(B).max()
+
+
+def _vec_close(T, Tref, nvar, ndim, tol):
+    if nvar == ndim:
+        assert np.linalg.norm(T - Tref) <= tol * max(np.linalg.norm(Tref), 1e-300)
+        return
+    mech = np.arange(T.shape[0]) % nvar != ndim
+    for m in (mech, ~mech):
+        assert np.linalg.norm((T - Tref)[m]) <= tol * max(np.linalg.norm(Tref[m]), 1e-300)
+
+
+@pytest.mark.parametrize("key", _cases())
+def test_assembly_against_oracle_and_golden(key):
+    from florence_b200 import backend
+    from oracle import oracle as orc
+    c = _load(key)
+    matname = key.split("_", 3)[3]
+    num = orc.MATERIAL_NUMBERS[matname]
+    nnode, ndim = c["points"].shape
+    electro = matname in ELEC
+    nvar = ndim + (1 if electro else 0)
+    form = 1 if electro else 0
+    H = orc.hessian_size(num, ndim)
+    n = nvar * nnode
+    update = int(c["update"])
+    h = backend.AssemblyHandle(c["points"], c["elements"], c["Jm"], c["AllGauss"], c["Bases"])
+    mat = _material(backend, num, c["prm"])
+
+    # --- sparsity pattern and slot maps: bit-exact against the reference's compiled ComputeSparsityPattern
+    indices, indptr, dl, dg = h.sparsity_pattern(nvar, with_data_indices=True)
+    assert indices.dtype == torch.int32 and indptr.dtype == torch.int32
+    assert np.array_equal(indices.cpu().numpy(), c["sp_indices"])
+    assert np.array_equal(indptr.cpu().numpy(), c["sp_indptr"])
+    if c["sp_dl"] is not None:
+        assert np.array_equal(dl.cpu().numpy(), c["sp_dl"])
+        assert np.array_equal(dg.cpu().numpy(), c["sp_dg"])
+
+    # --- implicit, COO mode
+    Io, Jo, Vo, To = orc.assemble_implicit(c["points"], c["elements"], c["Eulerx"], c["Eulerp"], c["Jm"], c["AllGauss"], nvar, H, update,
+                                           c["prm"], num, mode="coo")
+    I, J, V, T = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, update, mode="coo")
+    I, J, V, T = I.cpu().numpy(), J.cpu().numpy(), V.cpu().numpy(), T.cpu().numpy()
+    assert np.array_equal(I, Io) and np.array_equal(J, Jo)
+    Ko = csr_matrix((Vo, (Io, Jo)), shape=(n, n))
+    K = csr_matrix((V, (I, J)), shape=(n, n))
+    Kref = csr_matrix((c["K_data"], c["K_indices"], c["K_indptr"]), shape=(n, n))
+    _blockwise_close(K, Ko, nvar, ndim, 1e-10)
+    _blockwise_close(K, Kref, nvar, ndim, 1e-10)
+    _vec_close(T, To, nvar, ndim, 1e-11)
+    _vec_close(T, c["T"], nvar, ndim, 1e-11)
+    # per-entry check of the raw element matrices against the oracle
+    scale = np.abs(Vo).max() if not electro else None
+    if not electro:
+        assert np.abs(V - Vo).max() <= 1e-10 * scale
+
+    # --- implicit, CSR mode (deterministic node-centric reduction) equals the oracle's slot-map mode
+    pat = (c["sp_indices"], c["sp_indptr"], dl.cpu().numpy(), dg.cpu().numpy())
+    V1o, T1o = orc.assemble_implicit(c["points"], c["elements"], c["Eulerx"], c["Eulerp"], c["Jm"], c["AllGauss"], nvar, H, update,
+                                     c["prm"], num, mode="csr", pattern=pat)
+    V1, T1 = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, update, mode="csr")
+    V1b, _ = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, update, mode="csr")
+    assert torch.equal(V1, V1b), "CSR assembly must be bit-reproducible"
+    K1 = csr_matrix((V1.cpu().numpy(), c["sp_indices"], c["sp_indptr"]), shape=(n, n))
+    K1o = csr_matrix((V1o, c["sp_indices"], c["sp_indptr"]), shape=(n, n))
+    _blockwise_close(K1, K1o, nvar, ndim, 1e-10)
+    _vec_close(T1.cpu().numpy(), T1o, nvar, ndim, 1e-11)
+
+    # --- explicit (matrix-free) internal force
+    if update == 1:
+        Teo = orc.assemble_explicit(c["points"], c["elements"], c["Eulerx"], c["Eulerp"], c["Jm"], c["AllGauss"], nvar, c["prm"], num, form)
+        Te = h.assemble_explicit(c["Eulerx"], c["Eulerp"], mat, form).cpu().numpy()
+        _vec_close(Te, Teo, nvar, ndim, 1e-11)
+        _vec_close(Te, c["T"], nvar, ndim, 1e-11)
+    h.close()
+
+
+def test_explicit_only_materials():
+    """ExplicitMooneyRivlin (0) and ExplicitIsotropicElectroMechanics_108 (9): stress-only kernels of the explicit path."""
+    from florence_b200 import backend
+    from oracle import oracle as orc
+    for key, num, form in (("asm_hex2_n2_MooneyRivlin", 0, 0), ("asm_quad1_n3_MooneyRivlin", 0, 0),
+                           ("asm_hex2_n1_IsotropicElectroMechanics_108", 9, 1), ("asm_quad2_n2_IsotropicElectroMechanics_108", 9, 1)):
+        c = _load(key)
+        ndim = c["points"].shape[1]
+        nvar = ndim + form
+        h = backend.AssemblyHandle(c["points"], c["elements"], c["Jm"], c["AllGauss"], c["Bases"])
+        Teo = orc.assemble_explicit(c["points"], c["elements"], c["Eulerx"], c["Eulerp"], c["Jm"], c["AllGauss"], nvar, c["prm"], num, form)
+        Te = h.assemble_explicit(c["Eulerx"], c["Eulerp"], _material(backend, num, c["prm"]), form).cpu().numpy()
+        _vec_close(Te, Teo, nvar, ndim, 1e-11)
+        h.close()
+
+
+def test_unsupported_material_raises_not_implemented():
+    from florence_b200 import backend
+    c = _load("asm_hex1_n2_NeoHookean")
+    h = backend.AssemblyHandle(c["points"], c["elements"], c["Jm"], c["AllGauss"], c["Bases"])
+    with pytest.raises(NotImplementedError):
+        h.assemble_explicit(c["Eulerx"], None, backend.make_material(7), 0)
+    with pytest.raises(NotImplementedError):
+        h.assemble_implicit(c["Eulerx"], None, backend.make_material(0), 0, True, mode="coo")
+    with pytest.raises(ValueError):
+        h.assemble_explicit(c["Eulerx"], None, backend.make_material(8, mu1=1., mu2=1., lamb=1., eps_2=1.), 0)
+    h.close()
+
+
+def test_laplacian_against_oracle_and_golden():
+    from florence_b200 import backend
+    from oracle import oracle as orc
+    g = np.load(os.path.join(GOLD, "golden_laplacian.npz"))
+    for key in [str(s) for s in g["lap_cases"]]:
+        pts, els, Jm, AG, e = g[key + "_points"], g[key + "_elements"], g[key + "_Jm"], g[key + "_AllGauss"], g[key + "_e"]
+        n = pts.shape[0]
+        h = backend.AssemblyHandle(pts, els, Jm, AG)
+        Io, Jo, Vo = orc.assemble_laplacian(pts, els, Jm, AG, -e, True, mode="coo")
+        I, J, V = h.assemble_laplacian(-e, True, mode="coo")
+        assert np.array_equal(I.cpu().numpy(), Io) and np.array_equal(J.cpu().numpy(), Jo)
+        assert np.abs(V.cpu().numpy() - Vo).max() <= 1e-10 * np.abs(Vo).max(), key
+        Kref = csr_matrix((g[key + "_K_data"], g[key + "_K_indices"], g[key + "_K_indptr"]), shape=(n, n))
+        K = csr_matrix((V.cpu().numpy(), (Io, Jo)), shape=(n, n))
+        assert abs(K - Kref).max() <= 1e-10 * abs(Kref).max(), key
+        # non-symmetric branch and CSR mode
+        en = -e + 0.1 * np.triu(np.ones_like(e), 1)
+        Io, Jo, Vo = orc.assemble_laplacian(pts, els, Jm, AG, en, False, mode="coo")
+        V2 = h.assemble_laplacian(en, False, mode="coo")[2].cpu().numpy()
+        assert np.abs(V2 - Vo).max() <= 1e-10 * np.abs(Vo).max(), key
+        indices, indptr = h.sparsity_pattern(1)
+        Vc = h.assemble_laplacian(-e, True, mode="csr").cpu().numpy()
+        Kc = csr_matrix((Vc, indices.cpu().numpy(), indptr.cpu().numpy()), shape=(n, n))
+        assert abs(Kc - Kref).max() <= 1e-10 * abs(Kref).max(), key
+        h.close()
+
+
+def test_mass_lumped_and_consistent():
+    from florence_b200 import backend
+    from oracle import oracle as orc
+    g = np.load(os.path.join(GOLD, "golden_explicit.npz"))
+    pts, els, Jm, AG, Bases = g["exp_points"], g["exp_elements"], g["exp_Jm"], g["exp_AllGauss"], g["exp_Bases"]
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases)
+    M = h.assemble_mass(1100.0, 3, "lumped").cpu().numpy()
+    assert np.abs(M - g["exp_M_lumped"]).max() <= 1e-12 * np.abs(M).max()
+    Io, Jo, Vo = orc.assemble_mass(pts, els, Bases, Jm, AG, 3, 1100.0, "consistent")
+    I, J, V = h.assemble_mass(1100.0, 3, "consistent", mode="coo")
+    assert np.array_equal(I.cpu().numpy(), Io) and np.array_equal(J.cpu().numpy(), Jo)
+    assert np.abs(V.cpu().numpy() - Vo).max() <= 1e-12 * np.abs(Vo).max()
+    h.close()
+
+
+def test_explicit_time_loop_against_reference_trajectory():
+    """Device-resident central-difference loop against the trajectory the reference's own integrator produced."""
+    from florence_b200 import backend
+    g = np.load(os.path.join(GOLD, "golden_explicit.npz"))
+    pts, els, Jm, AG, Bases = g["exp_points"], g["exp_elements"], g["exp_Jm"], g["exp_AllGauss"], g["exp_Bases"]
+    prm, rho, dt, nsteps = g["exp_prm"], float(g["exp_rho"]), float(g["exp_dt"]), int(g["exp_nsteps"])
+    nnode = pts.shape[0]
+    ref = g["exp_TotalDisp"]
+    NF, AD = g["exp_neumann"], g["exp_applied_dirichlet"]
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases)
+    mat = _material(backend, 1, prm)
+    dev = h.device
+    M = h.assemble_mass(rho, 3, "lumped")
+    fixed = torch.zeros(nnode * 3, dtype=torch.uint8, device=dev)
+    fixed[torch.as_tensor(g["exp_columns_out"].astype(np.int64), device=dev)] = 1
+    X = torch.as_tensor(pts, device=dev).reshape(-1)
+    Eulerx = X.clone()
+    T = h.assemble_explicit(Eulerx.reshape(nnode, 3), None, mat, 0)
+    # start-up (ExplicitStructuralDynamicIntegrator.py:57-81), zero initial displacement and velocity
+    A0 = (torch.as_tensor(NF[:, 0], device=dev) - T) / M
+    U0 = torch.zeros_like(T)
+    U00 = (dt ** 2 / 2.) * A0
+    U00[fixed.bool()] = 0.0
+    incd = torch.zeros_like(T)
+    for inc in range(2, nsteps):
+        fext = torch.as_tensor(np.ascontiguousarray(NF[:, inc - 1]), device=dev)
+        incd.zero_()
+        incd[torch.as_tensor(g["exp_columns_out"].astype(np.int64), device=dev)] = torch.as_tensor(np.ascontiguousarray(AD[:, inc - 1]), device=dev)
+        status = h.explicit_steps(mat, dt, 1, inc, M, fext, fixed, incd, U0, U00, Eulerx, T, fext_scale0=1.0, fext_scale_step=0.0)
+        assert status == 0
+        U = (Eulerx - X).reshape(nnode, 3).cpu().numpy()
+        assert np.abs(U - ref[:, :, inc]).max() <= 1e-10 * np.abs(ref).max(), inc
+    h.close()
+
+
+def test_multi_step_fused_loop_equals_single_steps():
+    from florence_b200 import backend
+    c = _load("asm_hex2_n2_NeoHookean")
+    nnode = c["points"].shape[0]
+    h = backend.AssemblyHandle(c["points"], c["elements"], c["Jm"], c["AllGauss"], c["Bases"])
+    mat = _material(backend, 1, c["prm"])
+    dev = h.device
+    M = h.assemble_mass(1100.0, 3, "lumped")
+    fixed = torch.zeros(nnode * 3, dtype=torch.uint8, device=dev)
+    fixed[:9] = 1
+    fext = torch.zeros(nnode * 3, dtype=torch.float64, device=dev)
+    fext[-3:] = 50.0
+    dt = 2e-5
+
+    def run(chunks):
+        Eulerx = torch.as_tensor(c["Eulerx"], device=dev).reshape(-1).clone()
+        T = h.assemble_explicit(Eulerx.reshape(nnode, 3), None, mat, 0)
+        U0 = torch.zeros_like(T); U00 = torch.zeros_like(T)
+        inc = 2
+        for n in chunks:
+            assert h.explicit_steps(mat, dt, n, inc, M, fext, fixed, None, U0, U00, Eulerx, T, fext_scale0=0.0, fext_scale_step=0.01) == 0
+            inc += n
+        return Eulerx, T, U0, U00
+    a = run([1] * 12)
+    b = run([12])
+    cc = run([5, 7])
+    for x, y, z in zip(a, b, cc):
+        assert torch.equal(x, y) and torch.equal(x, z)
+    h.close()
