@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 assembly back end (contract: see the task statement / DESIGN.md section 6).
+
+Workload (config.workload): BASELINE.json configs[1] -- LinearElastic p=2 tetrahedra, 55^3 hexes split in 6 -> 998 250 tet10
+elements, 1 367 631 nodes, implicit stiffness + residual assembled to CSR (requires_geometry_update forced to 1 so that T is
+computed).  One "step" = one full assembly (K values in CSR order + T) of the whole mesh.
+  value : elements/s with the state already in HBM (CUDA events around K steps, max over ranks)
+  e2e   : the same assembly through the reference-facing plug-in function with HOST numpy state in and HOST K values / T out
+  roofline / roofline_fp64 : dominant kernel (implicit_elements_kernel) timed with CUDA events inside the library
+  cpu_baseline : the CPU restatement of the reference algorithm (oracle, -O3 -ffast-math) on a bounded sample, 1 core
+  explicit : secondary line for the metric's second half -- NeoHookean p=2 hex explicit dynamics, DOF-updates/s
+N > 1 (torchrun): weak scaling, every rank assembles its own slab (+1 halo layer of elements so the CSR rows of the nodes it
+owns are complete; no data-path collective); the explicit line exchanges interface forces over NCCL every step.
+`--impl reference` times the reference algorithm (oracle port) on all host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=55, help="hexes per edge before the 6-tet split (55 -> 998250 tet10)")
+    ap.add_argument("--explicit-n", type=int, default=160, help="hexes per edge of the hex27 explicit line (per GPU)")
+    ap.add_argument("--explicit-steps", type=int, default=20)
+    ap.add_argument("--no-explicit", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+MU, NU = 1.0e5, 0.3
+LAMB = 2.0 * MU * NU / (1.0 - 2.0 * NU)
+METRIC = "elements assembled/s (K+residual, fp64)"
+
+
+class Clocks(object):
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class _Obj(object):
+    pass
+
+
+def reference_objects(points, elements, Bases, Jm, AllGauss, ndim, nvar, recompute=False):
+    """Duck-typed stand-ins for (fem_solver, function_space, formulation, mesh, material) as the reference's wrappers read them."""
+    fs, fo, me, so = _Obj(), _Obj(), _Obj(), _Obj()
+    fs.Bases, fs.Jm, fs.AllGauss = Bases, Jm, AllGauss
+    fo.ndim, fo.nvar, fo.fields = ndim, nvar, "mechanics"
+    me.points, me.elements, me.nelem = points, elements, elements.shape[0]
+    me.ChangeType = lambda: None
+    so.recompute_sparsity_pattern, so.squeeze_sparsity_pattern, so.requires_geometry_update = recompute, False, True
+    return so, fs, fo, me
+
+
+# =================================================================================================== reference arm
+def run_reference(args, rank, world):
+    """The reference algorithm (CPU restatement; the Fastor/CBLAS build of Florence cannot be produced) on all host
+    cores: contiguous element blocks over a thread pool (the native call releases the GIL), COO triplets per block and
+    per-block T summed on the parent, then scipy COO->CSR -- the reference's own pool model (Assembly.py:936-1041)."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from scipy.sparse import csr_matrix
+    from florence_b200 import mesh as flmesh
+    from oracle import oracle as orc
+    orc.build()
+    cores = len(os.sched_getaffinity(0))
+    n = args.n
+    # bounded sample: a slab of the same mesh, ~cores * 30k elements per step
+    per_core = 30000
+    nz = max(1, min(n, int(round(cores * per_core / (6.0 * n * n)))))
+    pts, els = flmesh.box_tet_mesh(n, n, nz, p=2, lengths=(1.0, 1.0, float(nz) / n))
+    pts, els = pts.numpy(), els.numpy().astype(np.uint64)
+    Bases, Jm, AG = flmesh.tables("tet", 2)
+    rng = np.random.default_rng(0)
+    x = pts + 1e-3 * rng.uniform(-1, 1, pts.shape)
+    prm = orc.params(mu=MU, lamb=LAMB)
+    nelem, nnode = els.shape[0], pts.shape[0]
+    blocks = np.array_split(np.arange(nelem), cores)
+    ndof = 30
+
+    def work(b):
+        sub = els[b[0]:b[-1] + 1]
+        return orc.assemble_implicit(pts, sub, x, None, Jm, AG, 3, 6, 1, prm, 10, mode="coo", fast=True)
+
+    def step():
+        with ThreadPoolExecutor(cores) as ex:
+            res = list(ex.map(work, blocks))
+        I = np.concatenate([r[0] for r in res]); J = np.concatenate([r[1] for r in res]); V = np.concatenate([r[2] for r in res])
+        T = np.zeros(nnode * 3)
+        for r in res:
+            T += r[3]
+        K = csr_matrix((V, (I, J)), shape=(3 * nnode, 3 * nnode))
+        return K, T
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = nelem * steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "elements/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "tet10 LinearElastic implicit K(CSR)+T, %d^3 hexes x6 (reference arm: bounded slab sample)" % n},
+            "cpu_baseline": {"value": val, "unit": "elements/s", "cores": cores, "kind": "port",
+                             "sample": "%d tet10 elements per step (slab %dx%dx%d of the %d^3 mesh), %d thread-pool blocks, COO + scipy COO->CSR" %
+                                       (nelem, n, n, nz, n, cores)},
+            "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# =================================================================================================== B200 arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    from florence_b200 import assembly, backend, mesh as flmesh, partition, time_integrator
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    launches = 0
+    # ------------------------------------------------------------------ implicit tet10 (config 2)
+    n = args.n
+    halo = 1 if (world > 1 and rank < world - 1) else 0
+    pts, els = flmesh.box_tet_mesh(n, n, n + halo, p=2, lengths=(1.0, 1.0, float(n + halo) / n), device=dev)
+    pts[:, 2] += float(rank)  # slab `rank` of a box stacked along z
+    Bases, Jm, AG = flmesh.tables("tet", 2)
+    nelem_local, nnode = els.shape[0], pts.shape[0]
+    nelem_owned = 6 * n * n * n
+    h_edge = 1.0 / n
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    x = pts + 1e-3 * (2.0 * torch.rand(pts.shape, dtype=torch.float64, device=dev, generator=gen) - 1.0)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases, device=dev)
+    mat = backend.make_material(10, 0.0, mu=MU, lamb=LAMB)
+    nnz = h.build_pattern(3)
+    V = torch.empty(nnz, dtype=torch.float64, device=dev)
+    T = torch.empty(nnode * 3, dtype=torch.float64, device=dev)
+    ndof = 30
+    for _ in range(max(args.warmup, 3)):
+        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+    barrier()
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    launches += 3 * args.steps
+    value = nelem_owned * world * args.steps / (ms * 1e-3)
+    # per-kernel timing (events inside the library, same stream)
+    h.set_timing(True)
+    kms = []
+    for _ in range(args.steps):
+        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+        kms.append(h.get_timing())
+    h.set_timing(False)
+    launches += 3 * args.steps
+    clk = clocks.stop() if rank == 0 else None
+    kms = np.array(kms)
+    k_elem, k_csr, k_T = kms.mean(0)
+
+    # ------------------------------------------------------------------ e2e through the reference-facing plug-in (host in / host out)
+    x_host = x.cpu().numpy()
+    pts_host, els_host = pts.cpu().numpy(), els.cpu().numpy().astype(np.uint64)
+    so, fs, fo, me = reference_objects(pts_host, els_host, Bases, Jm, AG, 3, 3, recompute=False)
+    material = _Obj(); material.mu, material.lamb, material.rho, material.mtype = MU, LAMB, 1.0, "LinearElastic"
+    # pre-seed the handle cache with the handle that already holds this mesh (same mesh arrays -> no re-upload)
+    assembly._handle_cache[(assembly._array_key(pts_host), assembly._array_key(els_host), assembly._array_key(Jm))] = h
+    func = assembly._LowLevelAssemblyDF__LinearElastic_
+    for _ in range(2):
+        Vh, Th = func(so, fs, fo, me, material, x_host, None)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        Vh, Th = func(so, fs, fo, me, material, x_host, None)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    launches += 3 * (e2e_steps + 2)
+    e2e_value = nelem_owned * world * e2e_steps / e2e_s
+    h2d = x_host.nbytes
+    d2h = Vh.nbytes + Th.nbytes
+    assert np.array_equal(Vh, V.cpu().numpy()), "host path and device path disagree"
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    hbm_peak, peak_src = measured_peaks()
+    nnode_per_elem = nnode / float(nelem_local)
+    # B = 8 npe + (nnode/nelem)(2*8*d) + (nnode/nelem) 8 nvar + 4 ndof^2 + 8 nnz/nelem
+    B_alg = 8 * 10 + nnode_per_elem * (2 * 8 * 3) + nnode_per_elem * 8 * 3 + 4 * ndof * ndof + 8.0 * nnz / nelem_local
+    Fl_ref = 8 * (10 * 9 * 10 + 100 + 150 + (2 * 30 * 6 + 2 * 30)) + 8 * (2 * 36 * 30 + 2 * 6 * 900 + 2 * 900 + 25 * 100)
+    achieved_gbs = B_alg * nelem_local / (k_elem * 1e-3) / 1e9
+    dfma = backend.measure_fp64_peak(False, 20000)
+    launches += 4
+    roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None,
+            "kernel": "implicit_elements_kernel<3,LinearElastic,10>", "kernel_ms": float(k_elem), "peak_source": peak_src,
+            "algorithmic_bytes_per_element": B_alg, "share_of_step": float(k_elem / (k_elem + k_csr + k_T)),
+            "other_kernels_ms": {"csr_gather_kernel": float(k_csr), "gather_nodes_kernel": float(k_T)}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("implicit_elements_kernel_bytes_per_launch")
+        except Exception:
+            pass
+    roof64 = {"bound": "fp64", "achieved": Fl_ref * nelem_local / (k_elem * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
+              "frac": Fl_ref * nelem_local / (k_elem * 1e-3) / 1e12 / dfma, "flops_per_element_reference_count": Fl_ref,
+              "peak_source": "measured in this run (fl_measure_fp64_peak, register-resident DFMA loop)"}
+
+    line = {"metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "tet10 LinearElastic implicit K(CSR)+T, %d^3 hexes x6 = %d elements per GPU" % (n, nelem_owned),
+                       "nelem_per_gpu": nelem_owned, "halo_elements": nelem_local - nelem_owned, "nnode_per_gpu": nnode, "nnz_per_gpu": nnz,
+                       "mode": "CSR (recompute_sparsity_pattern=False), requires_geometry_update=1", "parallelism": "element slabs x%d" % world,
+                       "l2": "inputs+scratch (%.1f GB per step) larger than L2, no flush needed" % ((nelem_local * 900 * 8 * 2 + nnz * 8) / 1e9)},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "florence_b200.assembly._LowLevelAssemblyDF__LinearElastic_ (host numpy in, host numpy out)"},
+            "roofline": roof, "roofline_fp64": roof64}
+
+    # ------------------------------------------------------------------ cpu baseline (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.build()
+        ns = 200000
+        sub = els_host[:ns]
+        t0 = time.perf_counter()
+        orc.assemble_implicit(pts_host, sub, x_host, None, Jm, AG, 3, 6, 1, orc.params(mu=MU, lamb=LAMB), 10, mode="coo", fast=True)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "elements/s", "cores": 1, "kind": "port",
+                                "sample": "first %d elements of the same mesh, COO triplets + T, oracle -O3 -ffast-math, 1 thread (%.1f s)" % (ns, dt)}
+    del V, T, Vh, Th
+    h.close()
+    assembly._handle_cache.clear()
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ explicit hex27 NeoHookean line (config 3 shape, per-GPU slab)
+    if not args.no_explicit:
+        ne = args.explicit_n
+        part = partition.slab_partition_hex(ne, ne, ne, 2, rank, world, device=dev)
+        Bs, Jh, AGh = flmesh.tables("hex", 2)
+        hh = backend.AssemblyHandle(part.points, part.elements, Jh, AGh, Bs, device=dev)
+        mu, lamb, rho = 4.0e5, 2.0e6, 1100.0
+        mat_n = backend.make_material(1, rho, mu=mu, lamb=lamb)
+        ex = None
+        if world > 1:
+            pack, unpack = partition.device_pack_functions(hh)
+            ex = partition.InterfaceExchange(part, 3, dev, pack, unpack)
+        integ = time_integrator.ExplicitStructuralDynamicIntegrator(hh, mat_n, rho=rho, exchange=ex)
+        hx = 1.0 / ne
+        dt_x = 0.2 * hx / np.sqrt((lamb + 2 * mu) / rho)
+        nn = part.points.shape[0]
+        fixed = torch.zeros(nn * 3, dtype=torch.uint8, device=dev)
+        x0 = flmesh.perturbed_state(part.points, hx / 2, 0.02, seed=7)  # node spacing is h/2 at p=2
+        if ex is not None:
+            # interface nodes must start from the same perturbed position on both owners
+            x0 = part.points + 0.02 * (hx / 2) * torch.sin(1000.0 * part.points)
+        integ.initialise(part.points, None, fixed, dt_x)
+        integ.Eulerx.copy_(x0.reshape(-1)); integ.internal_force(integ.Eulerx.view(nn, 3), out=integ.T)
+        integ.step(3, 2)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        integ.step(args.explicit_steps, 5)
+        a1.record()
+        torch.cuda.synchronize()
+        ems = max_over_ranks(a0.elapsed_time(a1))
+        launches += 2 * (args.explicit_steps + 3) + 4
+        ndof_global = 3 * (2 * ne + 1) * (2 * ne + 1) * (2 * ne * world + 1)
+        hh.set_timing(True)
+        hh.assemble_explicit(integ.Eulerx.view(nn, 3), None, mat_n, 0)
+        t_el, _, t_g = hh.get_timing()
+        hh.set_timing(False)
+        nel = ne ** 3
+        B_x = 8 * 27 + (nn / nel) * (2 * 8 * 3) + (nn / nel) * 8 * 3
+        Fl_x = 27 * (10 * 9 * 27 + 100 + 500 + (2 * 81 * 6 + 2 * 81))
+        line["explicit"] = {"metric": "explicit DOF-updates/s", "value": ndof_global * args.explicit_steps / (ems * 1e-3), "unit": "DOF-updates/s",
+                            "elements_per_s": nel * world * args.explicit_steps / (ems * 1e-3), "ms_per_step": ems / args.explicit_steps,
+                            "steps": args.explicit_steps, "blew_up": bool(integ.blew_up()),
+                            "config": {"workload": "hex27 NeoHookean explicit central difference, %d^3 elements per GPU" % ne, "ndof": ndof_global,
+                                       "interface_bytes_per_step": 0 if ex is None else ex.bytes_per_exchange()},
+                            "roofline": {"bound": "hbm", "achieved": B_x * nel / (t_el * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": B_x * nel / (t_el * 1e-3) / 1e9 / hbm_peak, "kernel": "explicit_elements_kernel<3,NeoHookean>",
+                                         "kernel_ms": t_el, "gather_ms": t_g},
+                            "roofline_fp64": {"achieved": Fl_x * nel / (t_el * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
+                                              "frac": Fl_x * nel / (t_el * 1e-3) / 1e12 / dfma, "flops_per_element_reference_count": Fl_x}}
+        hh.close()
+    line["gpu_launches"] = int(launches)
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,294 @@
+"""Reference-facing plug-in layer: the functions Florence's assembly dispatch looks up, backed by the CUDA library.
+
+Mirrors Florence/FiniteElements/Assembly/_LowLevelAssembly_.py:45-141 (same names, arguments, return tuples and error
+behaviour) and the Cython wrappers it calls:
+    _LowLevelAssemblyDF__<Material>_ / _LowLevelAssemblyDPF__<Material>_   (_LowLevelAssemblyDF_.pyx:53-160, AOT_Assembler.py)
+    _LowLevelAssemblyExplicit_DF_DPF_                                       (_LowLevelAssemblyExplicit_DF_DPF_.pyx:44-152)
+    _LowLevelAssemblyPerfectLaplacian_                                      (_LowLevelAssemblyPerfectLaplacian_.pyx)
+    ComputeSparsityPattern                                                  (ComputeSparsityPattern.pyx:44-112)
+    __TotalConstantMassIntegrand__                                          (_MassIntegrand_.pyx:192-349)
+Objects are duck-typed exactly as the reference reads them.  Host arrays go to the device once per call
+(state) or once per mesh (cached handle); results come back as numpy / scipy objects, or stay on the device as torch
+tensors (DLPack-exportable) when `device_out=True`.
+"""
+import weakref
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+
+from . import backend
+from .backend import AssemblyHandle, MATERIAL_NUMBERS, make_material
+
+__all__ = ['_LowLevelAssembly_', '_LowLevelAssemblyExplicit_', '_LowLevelAssemblyLaplacian_']
+
+has_low_level_dispatcher = True
+
+# material -> constants read by the stamped wrappers (AOT_Assembler.py:109-117, :197-217) and by the explicit wrapper
+_CONSTANTS = {
+    "LinearElastic": ("mu", "lamb"),
+    "IncrementalLinearElastic": ("mu", "lamb"),
+    "NeoHookean": ("mu", "lamb"),
+    "MooneyRivlin": ("mu1", "mu2", "lamb"),
+    "ExplicitMooneyRivlin": ("mu1", "mu2", "lamb"),
+    "NearlyIncompressibleMooneyRivlin": (),  # (alpha, beta, kappa), see _material_struct
+    "IsotropicElectroMechanics_101": ("mu", "lamb", "eps_1"),
+    "IsotropicElectroMechanics_105": ("mu1", "mu2", "lamb", "eps_1", "eps_2"),
+    "IsotropicElectroMechanics_108": ("mu1", "mu2", "lamb", "eps_2"),
+    "ExplicitIsotropicElectroMechanics_108": ("mu1", "mu2", "lamb", "eps_2"),
+}
+_IMPLICIT_DF = ("LinearElastic", "IncrementalLinearElastic", "NeoHookean", "MooneyRivlin", "NearlyIncompressibleMooneyRivlin")
+_IMPLICIT_DPF = ("IsotropicElectroMechanics_101", "IsotropicElectroMechanics_105", "IsotropicElectroMechanics_108")
+
+
+def _material_struct(material, name=None):
+    name = name or getattr(material, "mtype", type(material).__name__)
+    if name not in MATERIAL_NUMBERS or name not in _CONSTANTS:
+        raise NotImplementedError("Low level assembly for material {} not available. Consider 'optimise=False' for now".format(name))
+    if name == "NearlyIncompressibleMooneyRivlin":
+        # the explicit wrapper passes (alpha, beta, kappa) in the (mu1, mu2, mu3) slots (.pyx:82-84)
+        consts = dict(mu1=material.alpha, mu2=material.beta, mu3=material.kappa)
+    else:
+        consts = {k: getattr(material, k) for k in _CONSTANTS[name]}
+    rho = getattr(material, "rho", 0.0)
+    return make_material(MATERIAL_NUMBERS[name], rho, **consts)
+
+
+# ------------------------------------------------------------------------------------------------ handle cache
+_handle_cache = {}
+
+
+def _array_key(a):
+    if isinstance(a, torch.Tensor):
+        return ("t", a.data_ptr(), tuple(a.shape))
+    a = np.asarray(a)
+    return ("n", a.__array_interface__["data"][0], a.shape)
+
+
+def get_handle(mesh, function_space):
+    """Device handle for (mesh, function_space); cached so repeated Newton / time steps do not re-upload the mesh."""
+    key = (_array_key(mesh.points), _array_key(mesh.elements), _array_key(function_space.Jm))
+    ent = _handle_cache.get(key)
+    if ent is not None:
+        return ent
+    if len(_handle_cache) >= 8:
+        _handle_cache.pop(next(iter(_handle_cache))).close()
+    h = AssemblyHandle(mesh.points, mesh.elements, function_space.Jm, function_space.AllGauss, getattr(function_space, "Bases", None))
+    _handle_cache[key] = h
+    return h
+
+
+def clear_handles():
+    for h in _handle_cache.values():
+        h.close()
+    _handle_cache.clear()
+
+
+_pinned = {}
+
+
+def _to_host(t, tag):
+    """D2H into a cached pinned buffer (returned as a numpy view of it)."""
+    key = (tag, t.dtype, t.numel())
+    buf = _pinned.get(key)
+    if buf is None:
+        if len(_pinned) > 16:
+            _pinned.clear()
+        buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        _pinned[key] = buf
+    buf.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
+
+
+def _state_to_device(h, Eulerx, Eulerp):
+    x = backend.to_device(Eulerx, torch.float64, h.device)
+    p = None if Eulerp is None else backend.to_device(Eulerp, torch.float64, h.device)
+    return x, p
+
+
+# ------------------------------------------------------------------------------------------------ stamped implicit assemblers
+def _implicit(matname, fields, fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp, device_out=False):
+    """Body of _LowLevelAssemblyDF_<Material>_ / _LowLevelAssemblyDPF_<Material>_ (.pyx:53-160)."""
+    h = get_handle(mesh, function_space)
+    mat = _material_struct(material, matname)
+    form = 1 if fields == "electro_mechanics" else 0
+    x, p = _state_to_device(h, Eulerx, Eulerp)
+    update = bool(fem_solver.requires_geometry_update)
+    if fem_solver.recompute_sparsity_pattern:
+        I, J, V, T = h.assemble_implicit(x, p, mat, form, update, mode="coo")
+        if device_out:
+            return I, J, V, T
+        return _to_host(I, "I"), _to_host(J, "J"), _to_host(V, "V"), _to_host(T, "T").copy()
+    V, T = h.assemble_implicit(x, p, mat, form, update, mode="csr")
+    if device_out:
+        return V, T
+    return _to_host(V, "V"), _to_host(T, "T").copy()
+
+
+def _stamp(matname, fields):
+    def assembler(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp, device_out=False):
+        return _implicit(matname, fields, fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp, device_out)
+    prefix = "_LowLevelAssemblyDPF__" if fields == "electro_mechanics" else "_LowLevelAssemblyDF__"
+    assembler.__name__ = prefix + matname + "_"
+    return assembler
+
+
+# the reference looks these names up in the module's globals() (_LowLevelAssembly_.py:47-60)
+for _m in _IMPLICIT_DF:
+    globals()["_LowLevelAssemblyDF__" + _m + "_"] = _stamp(_m, "mechanics")
+for _m in _IMPLICIT_DPF:
+    globals()["_LowLevelAssemblyDPF__" + _m + "_"] = _stamp(_m, "electro_mechanics")
+
+
+def _lookup(formulation, material):
+    prefix = "_LowLevelAssemblyDF__"
+    if formulation.fields == "electro_mechanics":
+        prefix = "_LowLevelAssemblyDPF__"
+    assembly_func = prefix + type(material).__name__ + "_"
+    if assembly_func not in globals():
+        raise NotImplementedError("Turning optimise option on for {} material is not supported yet. "
+                                  "Consider 'optimise=False' for now".format(type(material).__name__))
+    return globals()[assembly_func]
+
+
+def _LowLevelAssembly_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """_LowLevelAssembly_.py:45-83: returns (stiffness csr_matrix, T, F=[], mass=[])."""
+    func = _lookup(formulation, material)
+    nvar = formulation.nvar
+    mesh.ChangeType()
+    n = nvar * mesh.points.shape[0]
+    if fem_solver.recompute_sparsity_pattern:
+        I, J, V, T = func(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+        stiffness = csr_matrix((V, (I, J)), shape=(n, n), dtype=np.float64)
+    else:
+        V, T = func(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+        stiffness = csr_matrix((V, fem_solver.indices, fem_solver.indptr), shape=(n, n), dtype=np.float64)
+    F, mass = [], []
+    return stiffness, T, F, mass
+
+
+def _LowLevelAssembly_Par_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """_LowLevelAssembly_.py:87-105: the raw tuple of the stamped assembler."""
+    return _lookup(formulation, material)(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+
+
+# ------------------------------------------------------------------------------------------------ explicit
+def _LowLevelAssemblyExplicit_DF_DPF_(function_space, formulation, mesh, material, Eulerx, Eulerp, device_out=False):
+    """_LowLevelAssemblyExplicit_DF_DPF_.pyx:44-152: T (nnode*nvar)."""
+    h = get_handle(mesh, function_space)
+    mat = _material_struct(material)
+    if formulation.fields == "mechanics":
+        form = 0
+    elif formulation.fields == "electro_mechanics":
+        form = 1
+    else:
+        raise NotImplementedError("Explicit low level assembly for {} is not available".format(formulation.fields))
+    x, p = _state_to_device(h, Eulerx, Eulerp)
+    T = h.assemble_explicit(x, p, mat, form)
+    return T if device_out else _to_host(T, "Te").copy()
+
+
+def _LowLevelAssemblyExplicit_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """_LowLevelAssembly_.py:109-117."""
+    mesh.ChangeType()
+    T = _LowLevelAssemblyExplicit_DF_DPF_(function_space, formulation, mesh, material, Eulerx, Eulerp)
+    F, mass = [], []
+    return T, F, mass
+
+
+def _LowLevelAssemblyExplicit_Par_(function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """_LowLevelAssembly_.py:120-122."""
+    return _LowLevelAssemblyExplicit_DF_DPF_(function_space, formulation, mesh, material, Eulerx, Eulerp)
+
+
+# ------------------------------------------------------------------------------------------------ Laplacian
+def _LowLevelAssemblyPerfectLaplacian_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp, device_out=False):
+    """_LowLevelAssemblyPerfectLaplacian_.pyx: (I, J, V) or V."""
+    ndim = formulation.ndim
+    if material.e.shape[0] != ndim:
+        raise ValueError("Permittivity tensor has to have a size of (ndim x ndim)")
+    h = get_handle(mesh, function_space)
+    e = -np.asarray(material.e, dtype=np.float64)                       # .pyx:81
+    sym = bool(np.allclose(material.e, material.e.T, atol=1e-8))         # .pyx:82
+    if fem_solver.recompute_sparsity_pattern:
+        I, J, V = h.assemble_laplacian(e, sym, mode="coo")
+        return (I, J, V) if device_out else (_to_host(I, "I"), _to_host(J, "J"), _to_host(V, "V"))
+    V = h.assemble_laplacian(e, sym, mode="csr")
+    return V if device_out else _to_host(V, "V")
+
+
+def _LowLevelAssemblyLaplacian_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """_LowLevelAssembly_.py:126-141."""
+    mesh.GetNumberOfNodes()
+    mesh.ChangeType()
+    if fem_solver.recompute_sparsity_pattern:
+        I, J, V = _LowLevelAssemblyPerfectLaplacian_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+        stiffness = csr_matrix((V, (I, J)), shape=(mesh.nnode, mesh.nnode), dtype=np.float64)
+    else:
+        V = _LowLevelAssemblyPerfectLaplacian_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+        stiffness = csr_matrix((V, fem_solver.indices, fem_solver.indptr), shape=(mesh.nnode, mesh.nnode), dtype=np.float64)
+    return stiffness, np.zeros(mesh.nnode, np.float64)
+
+
+# ------------------------------------------------------------------------------------------------ pattern and mass
+def ComputeSparsityPattern(mesh, nvar, squeeze_sparsity_pattern=False, function_space=None, device_out=False):
+    """ComputeSparsityPattern.pyx:44-112: (indices, indptr[, data_local_indices, data_global_indices]), all int32."""
+    if function_space is None:
+        # the pattern does not depend on the tables; a 1-point dummy table lets the handle be built from the mesh alone
+        class _FS(object):
+            pass
+        function_space = _FS()
+        ndim, npe = mesh.points.shape[1], mesh.elements.shape[1]
+        function_space.Jm = np.zeros((ndim, npe, 1))
+        function_space.AllGauss = np.ones((1, 1))
+        function_space.Bases = np.zeros((npe, 1))
+        h = AssemblyHandle(mesh.points, mesh.elements, function_space.Jm, function_space.AllGauss, function_space.Bases)
+    else:
+        h = get_handle(mesh, function_space)
+    out = h.sparsity_pattern(nvar, with_data_indices=not squeeze_sparsity_pattern)
+    if device_out:
+        return out
+    return tuple(t.cpu().numpy() for t in out)
+
+
+def __TotalConstantMassIntegrand__(mesh, function_space, formulation, mass_type="lumped", recompute_sparsity_pattern=True,
+                                   squeeze_sparsity_pattern=False, indices=None, indptr=None, data_global_indices=None,
+                                   data_local_indices=None, rho=None, device_out=False):
+    """_MassIntegrand_.pyx:192-349.  rho is read from formulation.constant_mass_integrand's material in the reference; here it is
+    passed explicitly or taken from formulation.rho / formulation.material.rho."""
+    if rho is None:
+        rho = getattr(formulation, "rho", None)
+        if rho is None:
+            rho = formulation.material.rho
+    h = get_handle(mesh, function_space)
+    nvar = formulation.nvar
+    if mass_type == "lumped":
+        M = h.assemble_mass(rho, nvar, "lumped")
+        M = M if device_out else M.cpu().numpy()[:, None]
+        dummy = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.float64)
+        return (M,) + dummy if recompute_sparsity_pattern else (M, dummy[2])
+    if recompute_sparsity_pattern:
+        I, J, V = h.assemble_mass(rho, nvar, "consistent", mode="coo")
+        if not device_out:
+            I, J, V = I.cpu().numpy(), J.cpu().numpy(), V.cpu().numpy()
+        return np.zeros((1, 1)), I, J, V
+    V = h.assemble_mass(rho, nvar, "consistent", mode="csr")
+    return np.zeros((1, 1)), (V if device_out else V.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ drop-in installation
+def install(florence_module=None):
+    """Rebind Florence's low-level assembly entry points to this back end."""
+    if florence_module is None:
+        import Florence as florence_module
+    import sys
+    target = sys.modules[florence_module.__name__ + ".FiniteElements.Assembly._LowLevelAssembly_"]
+    asm = sys.modules[florence_module.__name__ + ".FiniteElements.Assembly.Assembly"]
+    for name in ("_LowLevelAssembly_", "_LowLevelAssembly_Par_", "_LowLevelAssemblyExplicit_", "_LowLevelAssemblyExplicit_Par_",
+                 "_LowLevelAssemblyLaplacian_"):
+        setattr(target, name, globals()[name])
+        if hasattr(asm, name):
+            setattr(asm, name, globals()[name])
+    target.has_low_level_dispatcher = True
+    return target

@@ -230,6 +230,21 @@ class AssemblyHandle(object):
                                               _ptr(inc_dirichlet), _ptr(T), _ptr(U0), _ptr(U00), _ptr(Eulerx), _ptr(nan_flag), _stream()))
 
 
+def _set_timing(self, enabled=True):
+    check(self.lib.fl_set_timing(self._h, 1 if enabled else 0))
+
+
+def _get_timing(self):
+    """(element kernel, stiffness scatter/reduction, nodal reduction) milliseconds of the last assembly call."""
+    ms = (C.c_float * 3)()
+    check(self.lib.fl_get_timing(self._h, ms))
+    return float(ms[0]), float(ms[1]), float(ms[2])
+
+
+AssemblyHandle.set_timing = _set_timing
+AssemblyHandle.get_timing = _get_timing
+
+
 def measure_fp64_peak(use_dmma=False, iters=20000):
     out = C.c_double(0.0)
     check(_lib.load().fl_measure_fp64_peak(1 if use_dmma else 0, iters, C.byref(out)))

@@ -144,8 +144,28 @@ int fl_create(const fl_mesh_desc* m, fl_handle** out) {
     return FL_OK;
 }
 
+static inline void mark(fl_handle* h, int k, cudaStream_t st) {
+    if (h->timing && h->ev[k]) cudaEventRecord(h->ev[k], st);
+}
+
+int fl_set_timing(fl_handle* h, int enabled) {
+    if (!h) { set_error("null handle"); return FL_ERR_INVALID; }
+    if (enabled && !h->ev[0])
+        for (int k = 0; k < 4; ++k) FL_CUDA_CHECK(cudaEventCreate(&h->ev[k]));
+    h->timing = enabled ? 1 : 0;
+    return FL_OK;
+}
+
+int fl_get_timing(fl_handle* h, float* ms) {
+    if (!h || !ms || !h->ev[0]) { set_error("timing is not enabled"); return FL_ERR_STATE; }
+    FL_CUDA_CHECK(cudaEventSynchronize(h->ev[3]));
+    for (int k = 0; k < 3; ++k) FL_CUDA_CHECK(cudaEventElapsedTime(&ms[k], h->ev[k], h->ev[k + 1]));
+    return FL_OK;
+}
+
 int fl_destroy(fl_handle* h) {
     if (!h) return FL_OK;
+    for (int k = 0; k < 4; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->bases); cudaFree(h->gw);
     cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank);
     cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag);
@@ -160,9 +180,14 @@ int fl_assemble_explicit(fl_handle* h, const double* Eulerx, const double* Euler
     const int nvar = h->ndim + (formulation_number == 1 ? 1 : 0);
     int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * h->npe * nvar);
     if (rc) return rc;
+    mark(h, 0, st);
     rc = launch_explicit_elements(h, Eulerx, Eulerp, mat, formulation_number, h->te, st);
     if (rc) return rc;
-    return launch_gather_nodes(h, nvar, h->te, T, st);
+    mark(h, 1, st);
+    mark(h, 2, st);
+    rc = launch_gather_nodes(h, nvar, h->te, T, st);
+    mark(h, 3, st);
+    return rc;
 }
 
 int fl_pattern_build(fl_handle* h, int nvar, int64_t* nnz_host) {
@@ -207,11 +232,16 @@ int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Euler
         if (rc) return rc;
         ke = h->ke;
     }
+    mark(h, 0, st);
     rc = launch_implicit_elements(h, Eulerx, Eulerp, mat, formulation_number, requires_geometry_update ? 1 : 0, ke, h->te, st);
     if (rc) return rc;
+    mark(h, 1, st);
     rc = scatter_stiffness(h, nvar, mode, ke, I, J, V, st);
     if (rc) return rc;
-    return launch_gather_nodes(h, nvar, h->te, T, st);
+    mark(h, 2, st);
+    rc = launch_gather_nodes(h, nvar, h->te, T, st);
+    mark(h, 3, st);
+    return rc;
 }
 
 int fl_assemble_laplacian(fl_handle* h, const double* e_tensor_host, int is_hessian_symmetric, int mode, int32_t* I, int32_t* J, double* V,

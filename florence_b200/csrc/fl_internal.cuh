@@ -55,6 +55,8 @@ struct fl_handle {
     int32_t* flag = nullptr;                       // device status word
     int sm_count = 148;
     int max_smem_optin = 0;
+    int timing = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace fl {

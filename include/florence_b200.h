@@ -138,6 +138,12 @@ int fl_explicit_update(fl_handle *h, double dt, double fext_scale, const double 
                        const double *inc_dirichlet, const double *T, double *U0, double *U00, double *Eulerx, int32_t *nan_flag_dev,
                        void *stream);
 
+/* Per-kernel device timing of the most recent fl_assemble_* call (CUDA events recorded on the call's stream):
+ * ms[0] = element kernel, ms[1] = stiffness scatter / CSR reduction, ms[2] = nodal (T) reduction.  Used by bench.py for
+ * the roofline of the dominant kernel.  fl_get_timing synchronises on the last event. */
+int fl_set_timing(fl_handle *h, int enabled);
+int fl_get_timing(fl_handle *h, float *ms3_host);
+
 /* fp64 pipe peaks of the device the roofline fractions are quoted against (measured, not nominal):
  * runs a register-resident DFMA loop / DMMA loop for `iters` iterations and returns TFLOP/s. */
 int fl_measure_fp64_peak(int use_dmma, int iters, double *tflops_host);
