@@ -20,11 +20,12 @@ namespace fl {
 
 constexpr int EXPL_THREADS = 256;
 
-template <int D, int MAT>
+template <int D, int MAT, int JM_SMEM>
 __global__ void __launch_bounds__(EXPL_THREADS)
 explicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                          const double* __restrict__ phi, const double* __restrict__ jm_g, const double* __restrict__ gw,
-                         int64_t nelem, int npe, int ng, int ldg, int EB, int jm_in_smem, MatParams prm, double* __restrict__ te) {
+                         int64_t nelem, int npe, int ng, int ldg, int EB, MatParams prm, double* __restrict__ te) {
+    constexpr int jm_in_smem = JM_SMEM;
     constexpr bool EL = mat_traits<MAT>::electro;
     constexpr int NV = D + (EL ? 1 : 0);
     constexpr int PS = D * NV;
@@ -76,14 +77,14 @@ explicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                     const double Xa = Xe[a * D + l], xa = xe[a * D + l];
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        JX[k * D + l] += j[k] * Xa;
-                        Jx[k * D + l] += j[k] * xa;
+                        JX[k * D + l] = fma(j[k], Xa, JX[k * D + l]);
+                        Jx[k * D + l] = fma(j[k], xa, Jx[k * D + l]);
                     }
                 }
                 if (EL) {
                     const double p = ph[el * npe + a];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) gp[k] += j[k] * p;
+                    for (int k = 0; k < D; ++k) gp[k] = fma(j[k], p, gp[k]);
                 }
             }
             double iJX[D * D], iJx[D * D];
@@ -97,7 +98,7 @@ explicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                 for (int l = 0; l < D; ++l) {
                     double v = 0;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) v += iJX[l * D + k] * Jx[k * D + i];
+                    for (int k = 0; k < D; ++k) v = fma(iJX[l * D + k], Jx[k * D + i], v);
                     F[i * D + l] = v;
                 }
             double E[D], Dv[D], sig[D * D];
@@ -134,18 +135,33 @@ explicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
         // phase 2: t_a = sum_g Jm_g[:,a]^T P_g
         for (int it = threadIdx.x; it < ne * npe; it += blockDim.x) {
             const int el = it / npe, a = it - el * npe;
-            double t[NV];
+            // two interleaved accumulator sets (even / odd Gauss points) shorten the dependent DFMA chains
+            double t[NV], u[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) t[i] = 0.0;
+            for (int i = 0; i < NV; ++i) t[i] = u[i] = 0.0;
             const double* Pe = Ps + el * ng * PS;
-            for (int g = 0; g < ng; ++g) {
+            int g = 0;
+            for (; g + 1 < ng; g += 2) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    const double j = jm[(k * npe + a) * ldg + g];
+                    const double j0 = jm[(k * npe + a) * ldg + g], j1 = jm[(k * npe + a) * ldg + g + 1];
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) t[i] += j * Pe[g * PS + k * NV + i];
+                    for (int i = 0; i < NV; ++i) {
+                        t[i] = fma(j0, Pe[g * PS + k * NV + i], t[i]);
+                        u[i] = fma(j1, Pe[(g + 1) * PS + k * NV + i], u[i]);
+                    }
                 }
             }
+            if (g < ng) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const double j0 = jm[(k * npe + a) * ldg + g];
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) t[i] = fma(j0, Pe[g * PS + k * NV + i], t[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) t[i] += u[i];
 #pragma unroll
             for (int i = 0; i < NV; ++i) te[(e0 * npe + it) * NV + i] = t[i];
         }
@@ -248,7 +264,7 @@ static int launch_expl(fl_handle* h, const double* Eulerx, const double* Eulerp,
         set_error("explicit kernel needs %zu bytes of shared memory", smem);
         return FL_ERR_UNSUPPORTED;
     }
-    auto kern = explicit_elements_kernel<D, MAT>;
+    auto kern = jm_in_smem ? explicit_elements_kernel<D, MAT, 1> : explicit_elements_kernel<D, MAT, 0>;
     FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EXPL_THREADS, smem));
@@ -256,8 +272,7 @@ static int launch_expl(fl_handle* h, const double* Eulerx, const double* Eulerp,
     const int64_t nbatch = (h->nelem + EB - 1) / EB;
     const int grid = (int)(nbatch < (int64_t)occ * h->sm_count ? nbatch : (int64_t)occ * h->sm_count);
     if (grid == 0) return FL_OK;
-    kern<<<grid, EXPL_THREADS, smem, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->gw, h->nelem, npe, ng, ldg, EB,
-                                           jm_in_smem ? 1 : 0, prm, te);
+    kern<<<grid, EXPL_THREADS, smem, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->gw, h->nelem, npe, ng, ldg, EB, prm, te);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }

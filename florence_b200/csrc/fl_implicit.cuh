@@ -28,33 +28,84 @@ struct impl_dims {
     static constexpr int SSZ = D * D + (EL ? D : 0);  // sigma*detJ (+ D*detJ)
 };
 
-template <int D, int MAT, int A>
+__host__ __device__ inline int odd_stride(int n) { return n | 1; }  // odd per-element strides: elements sharing a warp hit distinct banks
+
+// Shared-memory carve-up, identical on host (sizing) and device.
+template <int D, int MAT>
+struct impl_layout {
+    static constexpr bool EL = mat_traits<MAT>::electro;
+    static constexpr bool CONST_H = (MAT == MAT_LINEAR_ELASTIC);  // tangent independent of F: one copy per block
+    using dims = impl_dims<D, EL>;
+    int xstride, ijs, sgs, hss, sss, djs;
+    size_t jm_off, X_off, x_off, ph_off, iJ_off, SG_off, H_off, S_off, dJ_off, total;
+    __host__ __device__ impl_layout(int npe, int ng, int ldg, int EB, bool jm_in_smem) {
+        xstride = odd_stride(npe * D);
+        ijs = odd_stride(ng * D * D);
+        sgs = odd_stride(ng * npe * D);
+        hss = CONST_H ? 0 : odd_stride(ng * dims::HT * dims::HT);
+        sss = odd_stride(ng * dims::SSZ);
+        djs = odd_stride(ng);
+        size_t o = 0;
+        jm_off = o; o += jm_in_smem ? (size_t)D * npe * ldg : 0;
+        X_off = o; o += (size_t)EB * xstride;
+        x_off = o; o += (size_t)EB * xstride;
+        ph_off = o; o += EL ? (size_t)EB * npe : 0;
+        iJ_off = o; o += (size_t)EB * ijs;
+        SG_off = o; o += (size_t)EB * sgs;
+        H_off = o; o += CONST_H ? (size_t)dims::HT * dims::HT : (size_t)EB * hss;
+        S_off = o; o += (size_t)EB * sss;
+        dJ_off = o; o += (size_t)EB * djs;
+        total = o;
+    }
+};
+
+// SYM = 1: K_e = K_e^T (the Voigt tangent is symmetric by construction, Numeric.pyx:181-229, and so are B^T H B and the
+// geometric term), so a thread owning column (b,j) computes only the cyclic band of row nodes a = b, b+1, ..., b+npe/2 (mod npe)
+// and writes each block and its mirror image: half the fp64 work, same K_e layout.  SYM = 0 computes all rows.
+template <int D, int MAT, int A, int SYM, int JM_SMEM>
 __global__ void __launch_bounds__(IMPL_THREADS)
 implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                          const double* __restrict__ phi, const double* __restrict__ jm_g, const double* __restrict__ gw,
-                         int64_t nelem, int npe, int ng, int ldg, int EB, int jm_in_smem, int update, MatParams prm,
+                         int64_t nelem, int npe, int ng, int ldg, int EB, int update, MatParams prm,
                          double* __restrict__ ke, double* __restrict__ te) {
     constexpr bool EL = mat_traits<MAT>::electro;
     constexpr bool GEO = mat_traits<MAT>::geometric;
+    using L = impl_layout<D, MAT>;
+    constexpr bool CONST_H = L::CONST_H;
     using dims = impl_dims<D, EL>;
     constexpr int HT = dims::HT, NV = dims::NV, SSZ = dims::SSZ;
     extern __shared__ double smem[];
-    const int xstride = (npe * D) | 1;
-    double* jm_s = smem;
-    double* Xs = jm_s + (jm_in_smem ? D * npe * ldg : 0);
-    double* xs = Xs + EB * xstride;
-    double* ph = xs + EB * xstride;
-    double* iJ = ph + (EL ? EB * npe : 0);   // [el][g][D*D]  J_x^-1
-    double* SG = iJ + EB * ng * D * D;       // [el][g][a][D] spatial gradients
-    double* Hs = SG + EB * ng * npe * D;     // [el][g][HT*HT] hessian * detJ
-    double* Ss = Hs + EB * ng * HT * HT;     // [el][g][SSZ]   sigma * detJ, D * detJ
-    const double* jm = jm_in_smem ? jm_s : jm_g;
+    const L lay(npe, ng, ldg, EB, JM_SMEM);
+    double* jm_s = smem + lay.jm_off;
+    double* Xs = smem + lay.X_off;
+    double* xs = smem + lay.x_off;
+    double* ph = smem + lay.ph_off;
+    double* iJ = smem + lay.iJ_off;   // [el][g][D*D]  J_x^-1
+    double* SG = smem + lay.SG_off;   // [el][g][a][D] spatial gradients
+    double* Hs = smem + lay.H_off;    // [el][g][HT*HT] hessian * detJ   (CONST_H: one unscaled copy)
+    double* Ss = smem + lay.S_off;    // [el][g][SSZ]   sigma * detJ, D * detJ
+    double* dJ = smem + lay.dJ_off;   // [el][g]        detJ
+    const double* jm = JM_SMEM ? jm_s : jm_g;
+    const int xstride = lay.xstride;
     const int ndof = npe * NV;
-    const int nch = (npe + A - 1) / A;
+    const int half = npe / 2;
+    const int nrows = SYM ? half + 1 : npe;   // row nodes per column
+    const int nch = (nrows + A - 1) / A;
     const int tpe = nch * ndof;
 
-    if (jm_in_smem)
+    if (JM_SMEM)
         for (int i = threadIdx.x; i < D * npe * ldg; i += blockDim.x) jm_s[i] = jm_g[i];
+    if (CONST_H) {
+        // F-independent tangent (_LinearElastic_.h:46-51): evaluate once per block
+        if (threadIdx.x == 0) {
+            double F[D * D], sig[D * D], hess[HT * HT];
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) F[i] = (i % (D + 1) == 0) ? 1.0 : 0.0;
+            kinetic_measures<D, MAT, true>(F, nullptr, prm, sig, nullptr, hess);
+#pragma unroll
+            for (int i = 0; i < HT * HT; ++i) Hs[i] = hess[i];
+        }
+    }
 
     const int64_t nbatch = (nelem + EB - 1) / EB;
     for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
@@ -91,14 +142,14 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                     const double Xa = Xe[a * D + l], xa = xe[a * D + l];
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        JX[k * D + l] += j[k] * Xa;
-                        Jx[k * D + l] += j[k] * xa;
+                        JX[k * D + l] = fma(j[k], Xa, JX[k * D + l]);
+                        Jx[k * D + l] = fma(j[k], xa, Jx[k * D + l]);
                     }
                 }
                 if (EL) {
                     const double p = ph[el * npe + a];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) gp[k] += j[k] * p;
+                    for (int k = 0; k < D; ++k) gp[k] = fma(j[k], p, gp[k]);
                 }
             }
             double iJX[D * D], iJx[D * D];
@@ -113,7 +164,7 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                 for (int l = 0; l < D; ++l) {
                     double v = 0;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) v += iJX[l * D + k] * Jx[k * D + i];
+                    for (int k = 0; k < D; ++k) v = fma(iJX[l * D + k], Jx[k * D + i], v);
                     F[i * D + l] = v;
                 }
             double E[D], Dv[D], sig[D * D], hess[HT * HT];
@@ -122,39 +173,43 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                 for (int k = 0; k < D; ++k) {
                     double v = 0;
 #pragma unroll
-                    for (int jj = 0; jj < D; ++jj) v += iJx[k * D + jj] * gp[jj];
+                    for (int jj = 0; jj < D; ++jj) v = fma(iJx[k * D + jj], gp[jj], v);
                     E[k] = -v;
                 }
             }
-            kinetic_measures<D, MAT, true>(F, E, prm, sig, Dv, hess);
-            double* iJo = iJ + (el * ng + g) * D * D;
+            kinetic_measures<D, MAT, !CONST_H>(F, E, prm, sig, Dv, hess);
+            double* iJo = iJ + el * lay.ijs + g * D * D;
 #pragma unroll
             for (int i = 0; i < D * D; ++i) iJo[i] = iJx[i];
-            double* Ho = Hs + (el * ng + g) * HT * HT;
+            if (!CONST_H) {
+                double* Ho = Hs + el * lay.hss + g * HT * HT;
 #pragma unroll
-            for (int i = 0; i < HT * HT; ++i) Ho[i] = hess[i] * detJ;
-            double* So = Ss + (el * ng + g) * SSZ;
+                for (int i = 0; i < HT * HT; ++i) Ho[i] = hess[i] * detJ;
+            }
+            double* So = Ss + el * lay.sss + g * SSZ;
 #pragma unroll
             for (int i = 0; i < D * D; ++i) So[i] = sig[i] * detJ;
             if (EL) {
 #pragma unroll
                 for (int i = 0; i < D; ++i) So[D * D + i] = Dv[i] * detJ;
             }
+            dJ[el * lay.djs + g] = detJ;
         }
         __syncthreads();
         // ---- phase 2: spatial gradients grad_x N_a = J_x^-1 Jm_g[:,a]
         for (int it = threadIdx.x; it < ne * ng * npe; it += blockDim.x) {
-            const int a = it % npe, eg = it / npe, g = eg % ng;
-            const double* iJo = iJ + eg * D * D;
+            const int a = it % npe, eg = it / npe, g = eg % ng, el = eg / ng;
+            const double* iJo = iJ + el * lay.ijs + g * D * D;
             double j[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) j[k] = jm[(k * npe + a) * ldg + g];
+            double* sgo = SG + el * lay.sgs + (g * npe + a) * D;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 double v = 0;
 #pragma unroll
-                for (int jj = 0; jj < D; ++jj) v += iJo[k * D + jj] * j[jj];
-                SG[it * D + k] = v;
+                for (int jj = 0; jj < D; ++jj) v = fma(iJo[k * D + jj], j[jj], v);
+                sgo[k] = v;
             }
         }
         __syncthreads();
@@ -163,7 +218,7 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             const int el = it / tpe, r = it - el * tpe;
             const int chunk = r / ndof, col = r - chunk * ndof;
             const int b = col / NV, j = col - b * NV;
-            const int a0 = chunk * A;
+            const int r0 = chunk * A;
             // non-zero rows of column j of B_b and which gradient component sits there
             // (FillConstitutiveB_, _ConstitutiveStiffnessDF_.h:32-77, ...DPF_.h:42-96)
             int k0, k1, k2, c0, c1, c2;
@@ -178,54 +233,69 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                 else { k0 = 3; k1 = 4; c0 = 0; c1 = 1; }
                 k2 = 0; c2 = 0;
             }
+            // row nodes of this thread: a = b + r0 + aa (cyclic) when SYM, else a = r0 + aa
+            int arow[A];
+#pragma unroll
+            for (int aa = 0; aa < A; ++aa) {
+                int a = min(r0 + aa, nrows - 1) + (SYM ? b : 0);
+                if (a >= npe) a -= npe;
+                arow[aa] = a * D;
+            }
             double acc[A][NV];
 #pragma unroll
             for (int aa = 0; aa < A; ++aa)
 #pragma unroll
                 for (int i = 0; i < NV; ++i) acc[aa][i] = 0.0;
+            const double* sge = SG + el * lay.sgs;
             for (int g = 0; g < ng; ++g) {
-                const double* sg = SG + (size_t)(el * ng + g) * npe * D;
-                const double* Hg = Hs + (el * ng + g) * HT * HT;
-                const double w0 = sg[b * D + c0], w1 = sg[b * D + c1], w2 = (D == 3) ? sg[b * D + c2] : 0.0;
+                const double* sg = sge + g * npe * D;
+                const double* Hg = CONST_H ? Hs : Hs + el * lay.hss + g * HT * HT;
+                double w0 = sg[b * D + c0], w1 = sg[b * D + c1], w2 = (D == 3) ? sg[b * D + c2] : 0.0;
+                if (CONST_H) {
+                    const double d = dJ[el * lay.djs + g];
+                    w0 *= d; w1 *= d; w2 *= d;
+                }
                 double G[HT];
 #pragma unroll
                 for (int v = 0; v < HT; ++v) {
-                    double t = Hg[v * HT + k0] * w0 + Hg[v * HT + k1] * w1;
-                    if (D == 3) t += Hg[v * HT + k2] * w2;
+                    double t = Hg[v * HT + k0] * w0;
+                    t = fma(Hg[v * HT + k1], w1, t);
+                    if (D == 3) t = fma(Hg[v * HT + k2], w2, t);
                     G[v] = t;
                 }
                 double sb[D];
                 if (GEO) {
-                    // sigma*detJ applied to grad N_b, upper triangle of sigma as in _GeometricStiffness_.h:81-86
-                    const double* So = Ss + (el * ng + g) * SSZ;
+                    // sigma*detJ applied to grad N_b, upper triangle of sigma as in _GeometricStiffness_.h:81-86;
+                    // only the diagonal component i == j receives it, so fold the selection into sb
+                    const double* So = Ss + el * lay.sss + g * SSZ;
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
                         double t = 0;
 #pragma unroll
-                        for (int l = 0; l < D; ++l) t += (k <= l ? So[k * D + l] : So[l * D + k]) * sg[b * D + l];
+                        for (int l = 0; l < D; ++l) t = fma(k <= l ? So[k * D + l] : So[l * D + k], sg[b * D + l], t);
                         sb[k] = t;
                     }
                 }
 #pragma unroll
                 for (int aa = 0; aa < A; ++aa) {
-                    const int a = min(a0 + aa, npe - 1);
+                    const double* ap = sg + arow[aa];
                     double ag[D];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) ag[k] = sg[a * D + k];
+                    for (int k = 0; k < D; ++k) ag[k] = ap[k];
                     if (D == 3) {
-                        acc[aa][0] += ag[0] * G[0] + ag[1] * G[3] + ag[2] * G[4];
-                        acc[aa][1] += ag[1] * G[1] + ag[0] * G[3] + ag[2] * G[5];
-                        acc[aa][2] += ag[2] * G[2] + ag[0] * G[4] + ag[1] * G[5];
-                        if (EL) acc[aa][3] += ag[0] * G[6 % HT] + ag[1] * G[7 % HT] + ag[2] * G[8 % HT];
+                        acc[aa][0] = fma(ag[0], G[0], fma(ag[1], G[3], fma(ag[2], G[4], acc[aa][0])));
+                        acc[aa][1] = fma(ag[1], G[1], fma(ag[0], G[3], fma(ag[2], G[5], acc[aa][1])));
+                        acc[aa][2] = fma(ag[2], G[2], fma(ag[0], G[4], fma(ag[1], G[5], acc[aa][2])));
+                        if (EL) acc[aa][NV - 1] = fma(ag[0], G[6 % HT], fma(ag[1], G[7 % HT], fma(ag[2], G[8 % HT], acc[aa][NV - 1])));
                     } else {
-                        acc[aa][0] += ag[0] * G[0] + ag[1] * G[2];
-                        acc[aa][1] += ag[1] * G[1] + ag[0] * G[2];
-                        if (EL) acc[aa][2] += ag[0] * G[3 % HT] + ag[1] * G[4 % HT];
+                        acc[aa][0] = fma(ag[0], G[0], fma(ag[1], G[2], acc[aa][0]));
+                        acc[aa][1] = fma(ag[1], G[1], fma(ag[0], G[2], acc[aa][1]));
+                        if (EL) acc[aa][NV - 1] = fma(ag[0], G[3 % HT], fma(ag[1], G[4 % HT], acc[aa][NV - 1]));
                     }
                     if (GEO) {
                         double dum = 0;
 #pragma unroll
-                        for (int k = 0; k < D; ++k) dum += ag[k] * sb[k];
+                        for (int k = 0; k < D; ++k) dum = fma(ag[k], sb[k], dum);
 #pragma unroll
                         for (int i = 0; i < D; ++i) acc[aa][i] += (i == j) ? dum : 0.0;
                     }
@@ -234,10 +304,17 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             double* Ke = ke + (size_t)(e0 + el) * ndof * ndof;
 #pragma unroll
             for (int aa = 0; aa < A; ++aa) {
-                const int a = a0 + aa;
-                if (a < npe) {
+                // even npe: the last band row pairs b with b+npe/2, which both columns reach; only the lower one writes it
+                const bool dup = SYM && ((npe & 1) == 0) && (r0 + aa == half) && (b >= half);
+                if (r0 + aa < nrows && !dup) {
+                    const int a = arow[aa] / D;
 #pragma unroll
                     for (int i = 0; i < NV; ++i) Ke[(size_t)(a * NV + i) * ndof + col] = acc[aa][i];
+                    if (SYM && a != b) {
+                        // mirror image K[(b,j),(a,i)] = K[(a,i),(b,j)]
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) Ke[(size_t)col * ndof + a * NV + i] = acc[aa][i];
+                    }
                 }
             }
         }
@@ -249,20 +326,16 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             for (int i = 0; i < NV; ++i) t[i] = 0.0;
             if (update == 1) {
                 for (int g = 0; g < ng; ++g) {
-                    const double* ag = SG + ((size_t)(el * ng + g) * npe + a) * D;
-                    const double* So = Ss + (el * ng + g) * SSZ;
+                    const double* ag = SG + el * lay.sgs + (g * npe + a) * D;
+                    const double* So = Ss + el * lay.sss + g * SSZ;
 #pragma unroll
                     for (int i = 0; i < D; ++i) {
-                        double v = 0;
 #pragma unroll
-                        for (int l = 0; l < D; ++l) v += ag[l] * (l <= i ? So[l * D + i] : So[i * D + l]);
-                        t[i] += v;
+                        for (int l = 0; l < D; ++l) t[i] = fma(ag[l], l <= i ? So[l * D + i] : So[i * D + l], t[i]);
                     }
                     if (EL) {
-                        double v = 0;
 #pragma unroll
-                        for (int l = 0; l < D; ++l) v += ag[l] * So[D * D + l];
-                        t[NV - 1] += v;
+                        for (int l = 0; l < D; ++l) t[NV - 1] = fma(ag[l], So[D * D + l], t[NV - 1]);
                     }
                 }
             }
@@ -272,32 +345,10 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
     }
 }
 
-template <int D, int MAT, int A>
-int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, const MatParams& prm, int update, double* ke, double* te,
-                  cudaStream_t st) {
-    constexpr bool EL = mat_traits<MAT>::electro;
-    using dims = impl_dims<D, EL>;
-    const int npe = h->npe, ng = h->ng, ldg = h->ldg;
-    const int ndof = npe * dims::NV;
-    const int nch = (npe + A - 1) / A;
-    const int tpe = nch * ndof;
-    const int xstride = (npe * D) | 1;
-    const size_t jm_bytes = sizeof(double) * D * npe * ldg;
-    const size_t per_elem = sizeof(double) * ((size_t)2 * xstride + (EL ? npe : 0) + (size_t)ng * D * D + (size_t)ng * npe * D +
-                                              (size_t)ng * dims::HT * dims::HT + (size_t)ng * dims::SSZ);
-    const size_t limit = (size_t)h->max_smem_optin;
-    bool jm_in_smem = jm_bytes + per_elem <= limit && jm_bytes <= 64 * 1024;
-    if ((jm_in_smem ? jm_bytes : 0) + per_elem > limit) {
-        set_error("implicit kernel: one %d-node element needs %zu bytes of shared memory", npe, per_elem);
-        return FL_ERR_UNSUPPORTED;
-    }
-    // enough elements per batch to occupy the block in phase 3, within half the shared memory so two blocks fit per SM
-    int EB = (IMPL_THREADS + tpe - 1) / tpe;
-    if (EB < 1) EB = 1;
-    const size_t budget = limit / 2 > (jm_in_smem ? jm_bytes : 0) + per_elem ? limit / 2 : limit;
-    while (EB > 1 && (jm_in_smem ? jm_bytes : 0) + per_elem * EB > budget) --EB;
-    const size_t smem = (jm_in_smem ? jm_bytes : 0) + per_elem * EB;
-    auto kern = implicit_elements_kernel<D, MAT, A>;
+template <int D, int MAT, int A, int SYM, int JM_SMEM>
+int launch_impl_cfg(fl_handle* h, const double* Eulerx, const double* Eulerp, const MatParams& prm, int update, double* ke, double* te,
+                    cudaStream_t st, int EB, size_t smem) {
+    auto kern = implicit_elements_kernel<D, MAT, A, SYM, JM_SMEM>;
     FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, IMPL_THREADS, smem));
@@ -305,21 +356,48 @@ int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, cons
     const int64_t nbatch = (h->nelem + EB - 1) / EB;
     const int grid = (int)(nbatch < (int64_t)occ * h->sm_count ? nbatch : (int64_t)occ * h->sm_count);
     if (grid == 0) return FL_OK;
-    kern<<<grid, IMPL_THREADS, smem, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->gw, h->nelem, npe, ng, ldg, EB,
-                                           jm_in_smem ? 1 : 0, update, prm, ke, te);
+    kern<<<grid, IMPL_THREADS, smem, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->gw, h->nelem, h->npe, h->ng, h->ldg, EB, update,
+                                           prm, ke, te);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }
 
-// rows-per-thread chunk: whole element for tet10, 9 for hex27/quad9, 8 otherwise; electro uses 4-wide columns already
+template <int D, int MAT, int A>
+int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, const MatParams& prm, int update, double* ke, double* te,
+                  cudaStream_t st) {
+    constexpr bool EL = mat_traits<MAT>::electro;
+    using dims = impl_dims<D, EL>;
+    using L = impl_layout<D, MAT>;
+    const int npe = h->npe, ng = h->ng, ldg = h->ldg;
+    const int ndof = npe * dims::NV;
+    const int nrows = npe / 2 + 1;
+    const int tpe = ((nrows + A - 1) / A) * ndof;
+    const size_t limit = (size_t)h->max_smem_optin;
+    const size_t jm_bytes = sizeof(double) * D * npe * ldg;
+    bool jm_in_smem = jm_bytes <= 64 * 1024 && sizeof(double) * L(npe, ng, ldg, 1, true).total <= limit;
+    if (sizeof(double) * L(npe, ng, ldg, 1, jm_in_smem).total > limit) {
+        set_error("implicit kernel: one %d-node element needs %zu bytes of shared memory", npe, sizeof(double) * L(npe, ng, ldg, 1, false).total);
+        return FL_ERR_UNSUPPORTED;
+    }
+    // two phase-3 rounds worth of elements per batch (keeps phases 1-2 populated), within a quarter of the SM's shared memory
+    int EB = (2 * IMPL_THREADS) / tpe;
+    if (EB < 1) EB = 1;
+    while (EB > 1 && sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem).total > limit / 4) --EB;
+    const size_t smem = sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem).total;
+    return jm_in_smem ? launch_impl_cfg<D, MAT, A, 1, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem)
+                      : launch_impl_cfg<D, MAT, A, 1, 0>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+}
+
+// rows-per-thread chunk A over the band of npe/2+1 row nodes: 6 covers tet10 / tri6 / quad9 / hex8 in one pass, 7 splits hex27's
+// 14 rows in two, 11 splits hex64's 33 rows in three
 template <int D, int MAT>
 int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, const MatParams& prm, int update, double* ke, double* te,
                     cudaStream_t st) {
-    const int npe = h->npe;
-    if (npe <= 4) return launch_impl_A<D, MAT, 4>(h, Eulerx, Eulerp, prm, update, ke, te, st);
-    if (npe == 10) return launch_impl_A<D, MAT, 10>(h, Eulerx, Eulerp, prm, update, ke, te, st);
-    if (npe % 9 == 0) return launch_impl_A<D, MAT, 9>(h, Eulerx, Eulerp, prm, update, ke, te, st);
-    return launch_impl_A<D, MAT, 8>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+    const int rows = h->npe / 2 + 1;
+    if (rows <= 3) return launch_impl_A<D, MAT, 3>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+    if (rows <= 6) return launch_impl_A<D, MAT, 6>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+    if (rows % 7 == 0 || rows > 44) return launch_impl_A<D, MAT, 7>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+    return launch_impl_A<D, MAT, 11>(h, Eulerx, Eulerp, prm, update, ke, te, st);
 }
 
 template <int MAT>

@@ -270,59 +270,131 @@ int launch_coo_indices(fl_handle* h, int nvar, int32_t* I, int32_t* J, cudaStrea
     return FL_OK;
 }
 
-// V rows of node n = sum over its elements (ascending) of the K_e rows of n, placed by node rank (SparseAssemblyNativeCSR_)
-__global__ void csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
-                                  const int64_t* __restrict__ nbr_ptr, const uint16_t* __restrict__ rank, const double* __restrict__ ke,
-                                  int64_t nnode, int npe, int nvar, int wmax, double* __restrict__ V) {
+// V rows of node n = sum over its elements (ascending) of the K_e rows of n, placed by node rank (SparseAssemblyNativeCSR_).
+// The NV rows (a,0..NV-1) of K_e are adjacent, so one (element, node) visit is a single contiguous run of NV*ndof doubles.
+// Two visits are loaded per trip (independent loads in flight) and added in element order.
+template <int NV, int NPE>
+__global__ void __launch_bounds__(256)
+csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
+                  const uint16_t* __restrict__ rank, const double* __restrict__ ke, int64_t nnode, int npe_rt, int wmax,
+                  double* __restrict__ V) {
     extern __shared__ double rowbuf[];
+    const int npe = NPE ? NPE : npe_rt;
+    const int ndof = npe * NV;
+    const int run = NV * ndof;           // doubles per (element, node) visit
+    constexpr int MAXT = 4;              // register tile: up to 4*32 = 128 doubles per visit, else the generic loop
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int ndof = npe * nvar;
-    double* buf = rowbuf + (size_t)warp * nvar * wmax;
+    double* buf = rowbuf + (size_t)warp * NV * wmax;
     for (int64_t n = blockIdx.x * (int64_t)wpb + warp; n < nnode; n += (int64_t)gridDim.x * wpb) {
-        const int w = (int)(nbr_ptr[n + 1] - nbr_ptr[n]) * nvar;
-        for (int t = lane; t < nvar * w; t += 32) buf[t] = 0.0;
+        const int w = (int)(nbr_ptr[n + 1] - nbr_ptr[n]) * NV;
+        for (int t = lane; t < NV * w; t += 32) buf[t] = 0.0;
         __syncwarp();
-        const int64_t k1 = adj_ptr[n + 1];
-        for (int64_t k = adj_ptr[n]; k < k1; ++k) {
-            const int64_t flat = adj_idx[k];  // e*npe + a
-            const int64_t e = flat / npe;
-            const int a = (int)(flat - e * npe);
-            const uint16_t* rk = rank + flat * npe;
-            const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * nvar) * ndof;
-            for (int i = 0; i < nvar; ++i)
-                for (int c = lane; c < ndof; c += 32) {
-                    const int b = c / nvar, l = c - b * nvar;
-                    buf[i * w + (int)rk[b] * nvar + l] += krow[i * ndof + c];
+        const int64_t k0 = adj_ptr[n], k1 = adj_ptr[n + 1];
+        if (run <= MAXT * 32) {
+            // destination offsets depend only on (t, rank): i*w + rank[b]*NV + l
+            for (int64_t k = k0; k < k1; k += 2) {
+                const bool two = (k + 1 < k1);
+                const int64_t f0 = adj_idx[k], f1 = two ? adj_idx[k + 1] : f0;
+                const int64_t ea = f0 / npe, eb = f1 / npe;
+                const int aa = (int)(f0 - ea * npe), ab = (int)(f1 - eb * npe);
+                const double* ra = ke + ea * (int64_t)ndof * ndof + (int64_t)(aa * NV) * ndof;
+                const double* rb = ke + eb * (int64_t)ndof * ndof + (int64_t)(ab * NV) * ndof;
+                const uint16_t* qa = rank + f0 * npe;
+                const uint16_t* qb = rank + f1 * npe;
+                double va[MAXT], vb[MAXT];
+                int da[MAXT], db[MAXT];
+#pragma unroll
+                for (int u = 0; u < MAXT; ++u) {
+                    const int t = lane + 32 * u;
+                    if (t < run) {
+                        const int i = t / ndof, c = t - i * ndof;
+                        const int b = c / NV, l = c - b * NV;
+                        va[u] = ra[t];
+                        da[u] = i * w + (int)qa[b] * NV + l;
+                        if (two) {
+                            vb[u] = rb[t];
+                            db[u] = i * w + (int)qb[b] * NV + l;
+                        }
+                    }
                 }
-            __syncwarp();
+#pragma unroll
+                for (int u = 0; u < MAXT; ++u)
+                    if (lane + 32 * u < run) buf[da[u]] += va[u];
+                __syncwarp();
+                if (two) {
+#pragma unroll
+                    for (int u = 0; u < MAXT; ++u)
+                        if (lane + 32 * u < run) buf[db[u]] += vb[u];
+                    __syncwarp();
+                }
+            }
+        } else {
+            for (int64_t k = k0; k < k1; ++k) {
+                const int64_t flat = adj_idx[k];
+                const int64_t e = flat / npe;
+                const int a = (int)(flat - e * npe);
+                const uint16_t* rk = rank + flat * npe;
+                const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof;
+                for (int t = lane; t < run; t += 32) {
+                    const int i = t / ndof, c = t - i * ndof;
+                    const int b = c / NV, l = c - b * NV;
+                    buf[i * w + (int)rk[b] * NV + l] += krow[t];
+                }
+                __syncwarp();
+            }
         }
-        const int64_t base = nbr_ptr[n] * nvar * nvar;
-        for (int t = lane; t < nvar * w; t += 32) V[base + t] = buf[t];
+        const int64_t base = nbr_ptr[n] * NV * NV;
+        for (int t = lane; t < NV * w; t += 32) V[base + t] = buf[t];
         __syncwarp();
     }
 }
 
-int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st) {
+template <int NV, int NPE>
+static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     const Pattern& p = h->pat;
-    if (!p.nbr_ptr) { set_error("fl_pattern_build has not been called"); return FL_ERR_STATE; }
-    const int wmax = p.max_cnt * nvar;
-    const size_t per_warp = sizeof(double) * nvar * wmax;
+    const int wmax = p.max_cnt * NV;
+    const size_t per_warp = sizeof(double) * NV * wmax;
     int wpb = 8;
-    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    while (wpb > 1 && per_warp * wpb > 48 * 1024) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     if (smem > (size_t)h->max_smem_optin) {
         set_error("CSR row of %d entries does not fit shared memory", wmax);
         return FL_ERR_UNSUPPORTED;
     }
-    FL_CUDA_CHECK(cudaFuncSetAttribute(csr_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = csr_gather_kernel<NV, NPE>;
+    FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    if (occ < 1) occ = 1;
     int64_t blocks = (h->nnode + wpb - 1) / wpb;
-    const int64_t cap = (int64_t)h->sm_count * 16;
+    const int64_t cap = (int64_t)h->sm_count * occ * 4;
     if (blocks > cap) blocks = cap;
-    csr_gather_kernel<<<(unsigned)blocks, wpb * 32, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, nvar,
-                                                                wmax, V);
+    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, wmax, V);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
+}
+
+template <int NV>
+static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
+    switch (h->npe) {
+        case 4: return launch_csr_gather_T<NV, 4>(h, ke, V, st);
+        case 8: return launch_csr_gather_T<NV, 8>(h, ke, V, st);
+        case 10: return launch_csr_gather_T<NV, 10>(h, ke, V, st);
+        case 27: return launch_csr_gather_T<NV, 27>(h, ke, V, st);
+        default: return launch_csr_gather_T<NV, 0>(h, ke, V, st);
+    }
+}
+
+int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st) {
+    if (!h->pat.nbr_ptr) { set_error("fl_pattern_build has not been called"); return FL_ERR_STATE; }
+    switch (nvar) {
+        case 1: return launch_csr_gather_NV<1>(h, ke, V, st);
+        case 2: return launch_csr_gather_NV<2>(h, ke, V, st);
+        case 3: return launch_csr_gather_NV<3>(h, ke, V, st);
+        case 4: return launch_csr_gather_NV<4>(h, ke, V, st);
+        default: set_error("nvar=%d unsupported", nvar); return FL_ERR_INVALID;
+    }
 }
 
 }  // namespace fl
