@@ -19,6 +19,9 @@
 namespace fl {
 
 constexpr int IMPL_THREADS = 128;
+#ifndef FL_MINB_SPEC
+#define FL_MINB_SPEC 4
+#endif
 
 template <int D, bool EL>
 struct impl_dims {
@@ -35,10 +38,14 @@ template <int D, int MAT>
 struct impl_layout {
     static constexpr bool EL = mat_traits<MAT>::electro;
     static constexpr bool CONST_H = (MAT == MAT_LINEAR_ELASTIC);  // tangent independent of F: one copy per block
+    // isotropic constant tangent C = mu (I_ikjl + I_iljk) + lamb I_ijkl (_LinearElastic_.h:46-49): K_ab = lamb S + mu S^T + mu tr(S) I
+    // with S_ab = sum_g detJ grad N_a (x) grad N_b, i.e. 9 FMAs per Gauss point and node pair instead of 27 + the G product
+    static constexpr bool ISO = (MAT == MAT_LINEAR_ELASTIC);
+    static constexpr int AI = 3;  // row nodes per thread on the ISO path
     using dims = impl_dims<D, EL>;
     int xstride, ijs, sgs, hss, sss, djs;
-    size_t jm_off, X_off, x_off, ph_off, iJ_off, SG_off, H_off, S_off, dJ_off, total;
-    __host__ __device__ impl_layout(int npe, int ng, int ldg, int EB, bool jm_in_smem) {
+    size_t jm_off, X_off, x_off, ph_off, iJ_off, SG_off, H_off, S_off, dJ_off, K_off, total;
+    __host__ __device__ impl_layout(int npe, int ng, int ldg, int EB, bool jm_in_smem, bool stage = false) {
         xstride = odd_stride(npe * D);
         ijs = odd_stride(ng * D * D);
         sgs = odd_stride(ng * npe * D);
@@ -55,6 +62,9 @@ struct impl_layout {
         H_off = o; o += CONST_H ? (size_t)dims::HT * dims::HT : (size_t)EB * hss;
         S_off = o; o += (size_t)EB * sss;
         dJ_off = o; o += (size_t)EB * djs;
+        // K_e staging: the band mapping scatters a thread's blocks over rows, so K_e is assembled in shared memory and
+        // streamed out as one contiguous run per batch
+        K_off = o; o += stage ? (size_t)EB * (npe * dims::NV) * (npe * dims::NV) : 0;
         total = o;
     }
 };
@@ -62,12 +72,17 @@ struct impl_layout {
 // SYM = 1: K_e = K_e^T (the Voigt tangent is symmetric by construction, Numeric.pyx:181-229, and so are B^T H B and the
 // geometric term), so a thread owning column (b,j) computes only the cyclic band of row nodes a = b, b+1, ..., b+npe/2 (mod npe)
 // and writes each block and its mirror image: half the fp64 work, same K_e layout.  SYM = 0 computes all rows.
-template <int D, int MAT, int A, int SYM, int JM_SMEM>
-__global__ void __launch_bounds__(IMPL_THREADS)
+// NPE_T / NG_T > 0 fix nodes-per-element and Gauss-point counts at compile time for the hot element types (tet10, hex8,
+// hex27): the Gauss loop unrolls and every shared-memory address becomes base + immediate.  MINB is the occupancy target.
+template <int D, int MAT, int A, int SYM, int JM_SMEM, int NPE_T, int NG_T, int MINB, int STAGE>
+__global__ void __launch_bounds__(IMPL_THREADS, MINB)
 implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                          const double* __restrict__ phi, const double* __restrict__ jm_g, const double* __restrict__ gw,
-                         int64_t nelem, int npe, int ng, int ldg, int EB, int update, MatParams prm,
+                         int64_t nelem, int npe_rt, int ng_rt, int ldg_rt, int EB, int update, MatParams prm,
                          double* __restrict__ ke, double* __restrict__ te) {
+    const int npe = NPE_T ? NPE_T : npe_rt;
+    const int ng = NG_T ? NG_T : ng_rt;
+    const int ldg = NG_T ? (NG_T | 1) : ldg_rt;
     constexpr bool EL = mat_traits<MAT>::electro;
     constexpr bool GEO = mat_traits<MAT>::geometric;
     using L = impl_layout<D, MAT>;
@@ -75,7 +90,8 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
     using dims = impl_dims<D, EL>;
     constexpr int HT = dims::HT, NV = dims::NV, SSZ = dims::SSZ;
     extern __shared__ double smem[];
-    const L lay(npe, ng, ldg, EB, JM_SMEM);
+    const L lay(npe, ng, ldg, EB, JM_SMEM, STAGE);
+    double* Kst = smem + lay.K_off;
     double* jm_s = smem + lay.jm_off;
     double* Xs = smem + lay.X_off;
     double* xs = smem + lay.x_off;
@@ -90,8 +106,10 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
     const int ndof = npe * NV;
     const int half = npe / 2;
     const int nrows = SYM ? half + 1 : npe;   // row nodes per column
-    const int nch = (nrows + A - 1) / A;
-    const int tpe = nch * ndof;
+    constexpr bool ISO = L::ISO;
+    constexpr int AI = L::AI;
+    const int nch = ISO ? (nrows + AI - 1) / AI : (nrows + A - 1) / A;
+    const int tpe = ISO ? nch * npe : nch * ndof;
 
     if (JM_SMEM)
         for (int i = threadIdx.x; i < D * npe * ldg; i += blockDim.x) jm_s[i] = jm_g[i];
@@ -213,6 +231,74 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             }
         }
         __syncthreads();
+        // ---- phase 3 (isotropic constant tangent): S_ab = sum_g detJ grad N_a (x) grad N_b for column node b and AI row nodes
+        if constexpr (ISO) {
+            for (int it = threadIdx.x; it < ne * tpe; it += blockDim.x) {
+                const int el = it / tpe, r = it - el * tpe;
+                const int chunk = r / npe, b = r - chunk * npe;
+                const int r0 = chunk * AI;
+                int arow[AI];
+#pragma unroll
+                for (int aa = 0; aa < AI; ++aa) {
+                    int a = min(r0 + aa, nrows - 1) + (SYM ? b : 0);
+                    if (a >= npe) a -= npe;
+                    arow[aa] = a * D;
+                }
+                double S[AI][D][D];
+#pragma unroll
+                for (int aa = 0; aa < AI; ++aa)
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = 0; j < D; ++j) S[aa][i][j] = 0.0;
+                const double* sge = SG + el * lay.sgs;
+#pragma unroll(NG_T > 0 && NG_T <= 8 ? NG_T : 1)
+                for (int g = 0; g < ng; ++g) {
+                    const double* sg = sge + g * npe * D;
+                    const double d = dJ[el * lay.djs + g];
+                    double bg[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) bg[k] = sg[b * D + k] * d;
+#pragma unroll
+                    for (int aa = 0; aa < AI; ++aa) {
+                        const double* ap = sg + arow[aa];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            const double ai = ap[i];
+#pragma unroll
+                            for (int j = 0; j < D; ++j) S[aa][i][j] = fma(ai, bg[j], S[aa][i][j]);
+                        }
+                    }
+                }
+                double* Ke = STAGE ? Kst + (size_t)el * ndof * ndof : ke + (size_t)(e0 + el) * ndof * ndof;
+#pragma unroll
+                for (int aa = 0; aa < AI; ++aa) {
+                    const bool dup = SYM && ((npe & 1) == 0) && (r0 + aa == half) && (b >= half);
+                    if (r0 + aa < nrows && !dup) {
+                        const int a = arow[aa] / D;
+                        double tr = 0;
+#pragma unroll
+                        for (int i = 0; i < D; ++i) tr += S[aa][i][i];
+                        double Kb[D][D];
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = 0; j < D; ++j)
+                                Kb[i][j] = fma(prm.lamb, S[aa][i][j], prm.mu * S[aa][j][i]) + (i == j ? prm.mu * tr : 0.0);
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = 0; j < D; ++j) Ke[(size_t)(a * NV + i) * ndof + b * NV + j] = Kb[i][j];
+                        if (SYM && a != b) {
+#pragma unroll
+                            for (int j = 0; j < D; ++j)
+#pragma unroll
+                                for (int i = 0; i < D; ++i) Ke[(size_t)(b * NV + j) * ndof + a * NV + i] = Kb[i][j];
+                        }
+                    }
+                }
+            }
+        } else
         // ---- phase 3: column (b,j) of K_e for a chunk of A row nodes
         for (int it = threadIdx.x; it < ne * tpe; it += blockDim.x) {
             const int el = it / tpe, r = it - el * tpe;
@@ -247,6 +333,7 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
 #pragma unroll
                 for (int i = 0; i < NV; ++i) acc[aa][i] = 0.0;
             const double* sge = SG + el * lay.sgs;
+#pragma unroll(NG_T > 0 && NG_T <= 8 ? NG_T : 1)
             for (int g = 0; g < ng; ++g) {
                 const double* sg = sge + g * npe * D;
                 const double* Hg = CONST_H ? Hs : Hs + el * lay.hss + g * HT * HT;
@@ -301,7 +388,7 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                     }
                 }
             }
-            double* Ke = ke + (size_t)(e0 + el) * ndof * ndof;
+            double* Ke = STAGE ? Kst + (size_t)el * ndof * ndof : ke + (size_t)(e0 + el) * ndof * ndof;
 #pragma unroll
             for (int aa = 0; aa < A; ++aa) {
                 // even npe: the last band row pairs b with b+npe/2, which both columns reach; only the lower one writes it
@@ -342,13 +429,20 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
 #pragma unroll
             for (int i = 0; i < NV; ++i) te[(e0 * npe + it) * NV + i] = t[i];
         }
+        if (STAGE) {
+            // ---- phase 5: stream the staged element matrices of this batch out as one contiguous, fully coalesced run
+            __syncthreads();
+            double* dst = ke + (size_t)e0 * ndof * ndof;
+            const int tot = ne * ndof * ndof;
+            for (int t = threadIdx.x; t < tot; t += blockDim.x) dst[t] = Kst[t];
+        }
     }
 }
 
-template <int D, int MAT, int A, int SYM, int JM_SMEM>
+template <int D, int MAT, int A, int SYM, int JM_SMEM, int NPE_T, int NG_T, int MINB, int STAGE>
 int launch_impl_cfg(fl_handle* h, const double* Eulerx, const double* Eulerp, const MatParams& prm, int update, double* ke, double* te,
                     cudaStream_t st, int EB, size_t smem) {
-    auto kern = implicit_elements_kernel<D, MAT, A, SYM, JM_SMEM>;
+    auto kern = implicit_elements_kernel<D, MAT, A, SYM, JM_SMEM, NPE_T, NG_T, MINB, STAGE>;
     FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, IMPL_THREADS, smem));
@@ -371,7 +465,7 @@ int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, cons
     const int npe = h->npe, ng = h->ng, ldg = h->ldg;
     const int ndof = npe * dims::NV;
     const int nrows = npe / 2 + 1;
-    const int tpe = ((nrows + A - 1) / A) * ndof;
+    const int tpe = L::ISO ? ((nrows + L::AI - 1) / L::AI) * npe : ((nrows + A - 1) / A) * ndof;
     const size_t limit = (size_t)h->max_smem_optin;
     const size_t jm_bytes = sizeof(double) * D * npe * ldg;
     bool jm_in_smem = jm_bytes <= 64 * 1024 && sizeof(double) * L(npe, ng, ldg, 1, true).total <= limit;
@@ -379,13 +473,24 @@ int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, cons
         set_error("implicit kernel: one %d-node element needs %zu bytes of shared memory", npe, sizeof(double) * L(npe, ng, ldg, 1, false).total);
         return FL_ERR_UNSUPPORTED;
     }
-    // two phase-3 rounds worth of elements per batch (keeps phases 1-2 populated), within a quarter of the SM's shared memory
+    // stage K_e in shared memory when one element's matrix plus its Gauss data fits in half of the SM's shared memory
+    const bool stage = jm_in_smem && sizeof(double) * L(npe, ng, ldg, 1, true, true).total <= limit / 2;
+    // two phase-3 rounds worth of elements per batch (keeps phases 1-2 populated), within a fifth of the SM's shared memory
     int EB = (2 * IMPL_THREADS) / tpe;
     if (EB < 1) EB = 1;
-    while (EB > 1 && sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem).total > limit / 4) --EB;
-    const size_t smem = sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem).total;
-    return jm_in_smem ? launch_impl_cfg<D, MAT, A, 1, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem)
-                      : launch_impl_cfg<D, MAT, A, 1, 0>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+    while (EB > 1 && sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem, stage).total > limit / 5) --EB;
+    const size_t smem = sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem, stage).total;
+    // compile-time element shapes of the benchmark configs (mechanics, 3-D): tet10 (8 gp), hex8, hex27
+    if constexpr (D == 3 && !EL && A == 6) {
+        if (stage && npe == 10 && ng == 8) return launch_impl_cfg<D, MAT, A, 1, 1, 10, 8, FL_MINB_SPEC, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+        if (stage && npe == 8 && ng == 8) return launch_impl_cfg<D, MAT, A, 1, 1, 8, 8, FL_MINB_SPEC, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+    }
+    if constexpr (D == 3 && !EL && A == 7) {
+        if (stage && npe == 27 && ng == 27) return launch_impl_cfg<D, MAT, A, 1, 1, 27, 27, 4, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+    }
+    if (stage) return launch_impl_cfg<D, MAT, A, 1, 1, 0, 0, 4, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+    return jm_in_smem ? launch_impl_cfg<D, MAT, A, 1, 1, 0, 0, 4, 0>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem)
+                      : launch_impl_cfg<D, MAT, A, 1, 0, 0, 0, 4, 0>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
 }
 
 // rows-per-thread chunk A over the band of npe/2+1 row nodes: 6 covers tet10 / tri6 / quad9 / hex8 in one pass, 7 splits hex27's
