@@ -15,7 +15,7 @@ FL_MODE_COO, FL_MODE_CSR = 0, 1
 # every symbol include/florence_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ["fl_last_error", "fl_version", "fl_create", "fl_destroy", "fl_assemble_explicit", "fl_pattern_build", "fl_pattern_export",
            "fl_pattern_export_data_indices", "fl_assemble_implicit", "fl_assemble_laplacian", "fl_assemble_mass", "fl_explicit_steps",
-           "fl_pack_nodes", "fl_unpack_add_nodes", "fl_explicit_update", "fl_measure_fp64_peak", "fl_set_timing", "fl_get_timing"]
+           "fl_pack_nodes", "fl_unpack_add_nodes", "fl_explicit_update", "fl_measure_fp64_peak", "fl_set_timing", "fl_get_timing", "fl_set_option"]
 
 
 class MeshDesc(C.Structure):
@@ -66,6 +66,7 @@ def load():
     lib.fl_pack_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.fl_unpack_add_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.fl_explicit_update.argtypes = [vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fl_set_option.argtypes = [vp, i32, i32]
     lib.fl_set_timing.argtypes = [vp, i32]
     lib.fl_get_timing.argtypes = [vp, C.POINTER(C.c_float)]
     lib.fl_measure_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl)]

@@ -241,6 +241,11 @@ def _get_timing(self):
     return float(ms[0]), float(ms[1]), float(ms[2])
 
 
+def _set_option(self, option, value):
+    check(self.lib.fl_set_option(self._h, int(option), int(value)))
+
+
+AssemblyHandle.set_option = _set_option
 AssemblyHandle.set_timing = _set_timing
 AssemblyHandle.get_timing = _get_timing
 

@@ -148,6 +148,13 @@ static inline void mark(fl_handle* h, int k, cudaStream_t st) {
     if (h->timing && h->ev[k]) cudaEventRecord(h->ev[k], st);
 }
 
+int fl_set_option(fl_handle* h, int option, int value) {
+    if (!h) { set_error("null handle"); return FL_ERR_INVALID; }
+    if (option == 0) { h->use_mma = value ? 1 : 0; return FL_OK; }
+    set_error("unknown option %d", option);
+    return FL_ERR_INVALID;
+}
+
 int fl_set_timing(fl_handle* h, int enabled) {
     if (!h) { set_error("null handle"); return FL_ERR_INVALID; }
     if (enabled && !h->ev[0])

@@ -14,7 +14,7 @@
 // Thread mapping: phase 1 one thread per (element, Gauss point); phase 2 one thread per (element, node); elements are
 // packed back to back across the block so no lane idles for npe, ngauss < 32.  Per-element tractions are written to a
 // buffer and reduced per node in ascending element order (deterministic; the reference's summation order).
-#include "fl_internal.cuh"
+#include "fl_explicit_mma.cuh"
 
 namespace fl {
 
@@ -246,6 +246,11 @@ static int launch_expl(fl_handle* h, const double* Eulerx, const double* Eulerp,
     constexpr bool EL = mat_traits<MAT>::electro;
     constexpr int NV = D + (EL ? 1 : 0);
     const int npe = h->npe, ng = h->ng, ldg = h->ldg;
+    if constexpr (D == 3 && !EL) {
+        // fixed shapes of the benchmark configs run the tensor-core (DMMA) formulation
+        if (h->use_mma && npe == 27 && ng == 27) return launch_expl_mma<MAT, 27, 27, 8, 4, 4>(h, Eulerx, prm, te, st);
+        if (h->use_mma && npe == 8 && ng == 8) return launch_expl_mma<MAT, 8, 8, 32, 1, 1>(h, Eulerx, prm, te, st);
+    }
     const int per = npe > ng ? npe : ng;
     if (per > EXPL_THREADS) {
         set_error("element with %d nodes / %d gauss points exceeds the explicit kernel's block", npe, ng);

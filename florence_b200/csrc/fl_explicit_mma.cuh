@@ -1,0 +1,213 @@
+// fl_explicit_mma.cuh -- matrix-free internal force for 3-D mechanics on fixed element shapes, with both contractions
+// against the shared Jm table done on the fp64 tensor-core path (mma.sync m8n8k4 f64, DMMA).
+//
+// Same algebra as explicit_elements_kernel (fl_explicit.cu; reference _LowLevelAssemblyExplicit_DF_DPF_.h:458-717), regrouped
+// as two small GEMMs per batch of NE elements whose A operand is the SAME for every element:
+//   (1) Jac[(g,k), (e,c)]  = sum_a  Jm[k][a][g] * XX[a, (e,c)]        XX = [X | x] nodal coordinates, c = 0..5
+//   (2) t  [a,     (e,i)]  = sum_gk Jm[k][a][g] * P [(g,k), (e,i)]    P_g = w|J_x| J_x^-T sigma
+// Each warp keeps its A fragments (slices of the Jm table) in registers for the whole kernel; B fragments stream from
+// shared memory once per 8 output rows, so one shared-memory load feeds 256 FMAs instead of 1-2 in the scalar kernel.
+// Between the GEMMs one thread per (element, Gauss point) inverts the Jacobians and evaluates the material law.
+#pragma once
+#include "fl_internal.cuh"
+
+namespace fl {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int MMA_THREADS = 128;
+
+template <int NPE, int NG, int NE>
+struct mma_shape {
+    static constexpr int M1 = 3 * NG, K1 = NPE, N1 = 6 * NE;
+    static constexpr int M3 = NPE, K3 = 3 * NG, N3 = 3 * NE;
+    static constexpr int MT1 = (M1 + 7) / 8, KS1 = (K1 + 3) / 4, NT1 = N1 / 8;
+    static constexpr int MT3 = (M3 + 7) / 8, KS3 = (K3 + 3) / 4, NT3 = N3 / 8;
+    // leading dimensions == 8 (mod 16): the four 64-byte row segments of a B fragment tile two 128-byte wavefronts exactly
+    static constexpr int LDX = N1 + 8, LDP = N3 % 16 == 8 ? N3 : N3 + 8, LDJ = N1 + 2;
+    static constexpr int XX_SZ = KS1 * 4 * LDX, JAC_SZ = MT1 * 8 * LDJ, P_SZ = KS3 * 4 * LDP, TE_SZ = NE * NPE * 3;
+    static constexpr int SCR_SZ = JAC_SZ > TE_SZ ? JAC_SZ : TE_SZ;  // te staging aliases the Jacobian tile
+    static constexpr size_t SMEM = sizeof(double) * (size_t)(XX_SZ + SCR_SZ + P_SZ);
+};
+
+template <int MAT, int NPE, int NG, int NE, int WM1, int WM3>
+__global__ void __launch_bounds__(MMA_THREADS, 2)
+explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
+                             const double* __restrict__ jm, const double* __restrict__ gw, int64_t nelem, int ldg, MatParams prm,
+                             double* __restrict__ te) {
+    using S = mma_shape<NPE, NG, NE>;
+    constexpr int D = 3;
+    constexpr int WN1 = 4 / WM1, WN3 = 4 / WM3;
+    constexpr int MTW1 = (S::MT1 + WM1 - 1) / WM1, NTW1 = S::NT1 / WN1;
+    constexpr int MTW3 = (S::MT3 + WM3 - 1) / WM3, NTW3 = S::NT3 / WN3;
+    static_assert(S::NT1 % WN1 == 0 && S::NT3 % WN3 == 0, "n-tiles must split evenly over the warps");
+    extern __shared__ double smem[];
+    double* XXs = smem;                 // [KS1*4][LDX]   nodal coordinates, rows >= NPE stay zero
+    double* Scr = XXs + S::XX_SZ;       // [MT1*8][LDJ]   Jacobians, later [NE][NPE][3] tractions
+    double* Ps = Scr + S::SCR_SZ;       // [KS3*4][LDP]   P, rows >= 3 NG stay zero
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lr = lane >> 2, lc = lane & 3;  // fragment row group / thread-in-group
+    const int wm1 = warp % WM1, wn1 = warp / WM1, wm3 = warp % WM3, wn3 = warp / WM3;
+
+    // A fragments (row-major 8x4 tiles): a[r][c] lives in lane 4 r + c
+    double A1[MTW1][S::KS1], A3[MTW3][S::KS3];
+#pragma unroll
+    for (int j = 0; j < MTW1; ++j)
+#pragma unroll
+        for (int ks = 0; ks < S::KS1; ++ks) {
+            const int r = 8 * (wm1 + WM1 * j) + lr, a = 4 * ks + lc;
+            const int g = r / 3, k = r - 3 * g;
+            A1[j][ks] = (r < S::M1 && a < NPE) ? jm[(k * NPE + a) * ldg + g] : 0.0;
+        }
+#pragma unroll
+    for (int j = 0; j < MTW3; ++j)
+#pragma unroll
+        for (int ks = 0; ks < S::KS3; ++ks) {
+            const int a = 8 * (wm3 + WM3 * j) + lr, r = 4 * ks + lc;
+            const int g = r / 3, k = r - 3 * g;
+            A3[j][ks] = (a < NPE && r < S::K3) ? jm[(k * NPE + a) * ldg + g] : 0.0;
+        }
+    for (int i = threadIdx.x; i < S::XX_SZ; i += MMA_THREADS) XXs[i] = 0.0;
+    for (int i = threadIdx.x; i < S::P_SZ; i += MMA_THREADS) Ps[i] = 0.0;
+
+    const int64_t nbatch = (nelem + NE - 1) / NE;
+    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int64_t e0 = batch * NE;
+        const int ne = (int)min((int64_t)NE, nelem - e0);
+        __syncthreads();
+        // gather [X | x] of the batch: XXs[a][e*6 + c]
+        for (int it = threadIdx.x; it < NE * NPE; it += MMA_THREADS) {
+            const int el = it / NPE, a = it - el * NPE;
+            double v[6] = {0, 0, 0, 0, 0, 0};
+            if (el < ne) {
+                const int64_t n = conn[e0 * NPE + it];
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    v[l] = X[n * 3 + l];
+                    v[3 + l] = x[n * 3 + l];
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 6; ++l) XXs[a * S::LDX + el * 6 + l] = v[l];
+        }
+        __syncthreads();
+        // ---- GEMM 1: Jacobians
+#pragma unroll 1
+        for (int jn = 0; jn < NTW1; ++jn) {
+            const int nt = wn1 + WN1 * jn;
+            double c[MTW1][2];
+#pragma unroll
+            for (int j = 0; j < MTW1; ++j) c[j][0] = c[j][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < S::KS1; ++ks) {
+                const double b = XXs[(4 * ks + lc) * S::LDX + 8 * nt + lr];
+#pragma unroll
+                for (int j = 0; j < MTW1; ++j) dmma884(c[j][0], c[j][1], A1[j][ks], b);
+            }
+#pragma unroll
+            for (int j = 0; j < MTW1; ++j) {
+                const int mt = wm1 + WM1 * j;
+                if (mt < S::MT1) {
+                    double* o = Scr + (8 * mt + lr) * S::LDJ + 8 * nt + 2 * lc;
+                    o[0] = c[j][0];
+                    o[1] = c[j][1];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- kinematics + constitutive law at (element, Gauss point)
+        for (int it = threadIdx.x; it < NE * NG; it += MMA_THREADS) {
+            const int el = it / NG, g = it - el * NG;
+            double Pv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (el < ne) {
+                double JX[9], Jx[9];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        JX[k * 3 + l] = Scr[(g * 3 + k) * S::LDJ + el * 6 + l];
+                        Jx[k * 3 + l] = Scr[(g * 3 + k) * S::LDJ + el * 6 + 3 + l];
+                    }
+                double iJX[9], iJx[9];
+                invdet(JX, iJX);
+                const double detx = invdet(Jx, iJx);
+                const double detJ = gw[g] * fabs(detx);
+                double F[9];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        double v = 0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) v = fma(iJX[l * 3 + k], Jx[k * 3 + i], v);
+                        F[i * 3 + l] = v;
+                    }
+                double sig[9];
+                kinetic_measures<D, MAT, false>(F, nullptr, prm, sig, nullptr, nullptr);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        double v = 0;
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj) v = fma(iJx[jj * 3 + k], (jj <= i ? sig[jj * 3 + i] : sig[i * 3 + jj]), v);
+                        Pv[k * 3 + i] = v * detJ;
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) Ps[(g * 3 + k) * S::LDP + el * 3 + i] = Pv[k * 3 + i];
+        }
+        __syncthreads();
+        // ---- GEMM 2: nodal tractions, staged in shared memory in te layout [e][a][i]
+#pragma unroll 1
+        for (int jn = 0; jn < NTW3; ++jn) {
+            const int nt = wn3 + WN3 * jn;
+            double c[MTW3][2];
+#pragma unroll
+            for (int j = 0; j < MTW3; ++j) c[j][0] = c[j][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < S::KS3; ++ks) {
+                const double b = Ps[(4 * ks + lc) * S::LDP + 8 * nt + lr];
+#pragma unroll
+                for (int j = 0; j < MTW3; ++j) dmma884(c[j][0], c[j][1], A3[j][ks], b);
+            }
+#pragma unroll
+            for (int j = 0; j < MTW3; ++j) {
+                const int a = 8 * (wm3 + WM3 * j) + lr;
+                if (a < NPE) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int n = 8 * nt + 2 * lc + q;
+                        const int el = n / 3, i = n - 3 * el;
+                        Scr[el * (NPE * 3) + a * 3 + i] = c[j][q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        double* dst = te + (size_t)e0 * NPE * 3;
+        for (int t = threadIdx.x; t < ne * NPE * 3; t += MMA_THREADS) dst[t] = Scr[t];
+    }
+}
+
+template <int MAT, int NPE, int NG, int NE, int WM1, int WM3>
+int launch_expl_mma(fl_handle* h, const double* Eulerx, const MatParams& prm, double* te, cudaStream_t st) {
+    using S = mma_shape<NPE, NG, NE>;
+    auto kern = explicit_elements_mma_kernel<MAT, NPE, NG, NE, WM1, WM3>;
+    FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    int occ = 1;
+    FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_THREADS, S::SMEM));
+    if (occ < 1) occ = 1;
+    const int64_t nbatch = (h->nelem + NE - 1) / NE;
+    const int grid = (int)(nbatch < (int64_t)occ * h->sm_count ? nbatch : (int64_t)occ * h->sm_count);
+    if (grid == 0) return FL_OK;
+    kern<<<grid, MMA_THREADS, S::SMEM, st>>>(h->conn, h->points, Eulerx, h->jm, h->gw, h->nelem, h->ldg, prm, te);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+}  // namespace fl

@@ -19,6 +19,12 @@
 namespace fl {
 
 constexpr int IMPL_THREADS = 128;
+#ifndef FL_AI
+#define FL_AI 3
+#endif
+#ifndef FL_EB_DIV
+#define FL_EB_DIV 5
+#endif
 #ifndef FL_MINB_SPEC
 #define FL_MINB_SPEC 4
 #endif
@@ -41,7 +47,7 @@ struct impl_layout {
     // isotropic constant tangent C = mu (I_ikjl + I_iljk) + lamb I_ijkl (_LinearElastic_.h:46-49): K_ab = lamb S + mu S^T + mu tr(S) I
     // with S_ab = sum_g detJ grad N_a (x) grad N_b, i.e. 9 FMAs per Gauss point and node pair instead of 27 + the G product
     static constexpr bool ISO = (MAT == MAT_LINEAR_ELASTIC);
-    static constexpr int AI = 3;  // row nodes per thread on the ISO path
+    static constexpr int AI = FL_AI;  // row nodes per thread on the ISO path
     using dims = impl_dims<D, EL>;
     int xstride, ijs, sgs, hss, sss, djs;
     size_t jm_off, X_off, x_off, ph_off, iJ_off, SG_off, H_off, S_off, dJ_off, K_off, total;
@@ -478,7 +484,7 @@ int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, cons
     // two phase-3 rounds worth of elements per batch (keeps phases 1-2 populated), within a fifth of the SM's shared memory
     int EB = (2 * IMPL_THREADS) / tpe;
     if (EB < 1) EB = 1;
-    while (EB > 1 && sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem, stage).total > limit / 5) --EB;
+    while (EB > 1 && sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem, stage).total > limit / FL_EB_DIV) --EB;
     const size_t smem = sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem, stage).total;
     // compile-time element shapes of the benchmark configs (mechanics, 3-D): tet10 (8 gp), hex8, hex27
     if constexpr (D == 3 && !EL && A == 6) {

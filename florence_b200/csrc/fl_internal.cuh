@@ -56,6 +56,7 @@ struct fl_handle {
     int sm_count = 148;
     int max_smem_optin = 0;
     int timing = 0;
+    int use_mma = 1;             // explicit path: DMMA kernels for hex8 / hex27 (fl_set_option)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -33,7 +33,9 @@ if n_hex:
         h.set_timing(True)
         for name, num, prm in (("NeoHookean", 1, dict(mu=4e5, lamb=2e6)), ("MooneyRivlin", 2, dict(mu1=2e5, mu2=2e5, lamb=2e6))):
             mat = backend.make_material(num, 1100.0, **prm)
-            T = h.assemble_explicit(x, None, mat, 0)
-            t = med(lambda: h.assemble_explicit(x, None, mat, 0, out=T))
-            print("hex p=%d %s explicit: nelem=%d elem=%.3f ms gather=%.3f ms -> %.1f Melem/s" % (p, name, els.shape[0], t[0], t[2], els.shape[0] / (t[0] + t[2]) / 1e3))
+            for mma in (1, 0):
+                h.set_option(0, mma)
+                T = h.assemble_explicit(x, None, mat, 0)
+                t = med(lambda: h.assemble_explicit(x, None, mat, 0, out=T))
+                print("hex p=%d %s explicit (dmma=%d): nelem=%d elem=%.3f ms gather=%.3f ms -> %.1f Melem/s" % (p, name, mma, els.shape[0], t[0], t[2], els.shape[0] / (t[0] + t[2]) / 1e3))
         h.close()

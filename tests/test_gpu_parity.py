@@ -260,3 +260,27 @@ def test_multi_step_fused_loop_equals_single_steps():
     for x, y, z in zip(a, b, cc):
         assert torch.equal(x, y) and torch.equal(x, z)
     h.close()
+
+
+@pytest.mark.parametrize("p,n", [(2, 5), (1, 7)])
+def test_explicit_tensor_core_kernel_equals_scalar_kernel_and_oracle(p, n):
+    """hex8 / hex27 mechanics run the DMMA formulation; it must agree with the scalar kernel and the oracle, including
+    batches that are only partly filled (nelem not a multiple of the batch size)."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    pts, els = flmesh.box_hex_mesh(n, n - 1, n + 1, p=p)
+    Bases, Jm, AG = flmesh.tables("hex", p)
+    x = flmesh.perturbed_state(pts, 1.0 / (p * n), 0.05, seed=5)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases)
+    for num, prm in ((1, dict(mu=4e5, lamb=2e6)), (2, dict(mu1=2e5, mu2=1e5, lamb=2e6)), (0, dict(mu1=2e5, mu2=1e5, lamb=2e6)),
+                     (3, dict(mu1=2e5, mu2=3e4, mu3=2.3e6)), (10, dict(mu=4e5, lamb=2e6))):
+        mat = backend.make_material(num, 0.0, **prm)
+        To = orc.assemble_explicit(pts.numpy(), els.numpy(), x.numpy(), None, Jm, AG, 3, orc.params(**prm), num)
+        h.set_option(0, 1)
+        T1 = h.assemble_explicit(x, None, mat, 0).cpu().numpy()
+        h.set_option(0, 0)
+        T0 = h.assemble_explicit(x, None, mat, 0).cpu().numpy()
+        assert np.linalg.norm(T1 - To) <= 1e-11 * np.linalg.norm(To)
+        assert np.linalg.norm(T0 - To) <= 1e-11 * np.linalg.norm(To)
+        assert np.abs(T1 - T0).max() <= 1e-11 * np.abs(To).max()
+    h.close()
