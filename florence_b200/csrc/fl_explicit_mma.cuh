@@ -29,7 +29,7 @@ struct mma_shape {
     static constexpr int LDX = N1 + 8, LDP = N3 % 16 == 8 ? N3 : N3 + 8, LDJ = N1 + 2;
     static constexpr int XX_SZ = KS1 * 4 * LDX, JAC_SZ = MT1 * 8 * LDJ, P_SZ = KS3 * 4 * LDP, TE_SZ = NE * NPE * 3;
     static constexpr int SCR_SZ = JAC_SZ > TE_SZ ? JAC_SZ : TE_SZ;  // te staging aliases the Jacobian tile
-    static constexpr size_t SMEM = sizeof(double) * (size_t)(XX_SZ + SCR_SZ + P_SZ);
+    static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * XX_SZ + SCR_SZ + P_SZ);  // coordinates are double-buffered
 };
 
 template <int MAT, int NPE, int NG, int NE, int WM1, int WM3>
@@ -43,9 +43,11 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
     constexpr int MTW1 = (S::MT1 + WM1 - 1) / WM1, NTW1 = S::NT1 / WN1;
     constexpr int MTW3 = (S::MT3 + WM3 - 1) / WM3, NTW3 = S::NT3 / WN3;
     static_assert(S::NT1 % WN1 == 0 && S::NT3 % WN3 == 0, "n-tiles must split evenly over the warps");
+    constexpr int NB1 = (NTW1 % 3 == 0) ? 3 : (NTW1 % 2 == 0 ? 2 : 1);
+    constexpr int GI = (NE * NPE + MMA_THREADS - 1) / MMA_THREADS;  // gather items per thread
     extern __shared__ double smem[];
-    double* XXs = smem;                 // [KS1*4][LDX]   nodal coordinates, rows >= NPE stay zero
-    double* Scr = XXs + S::XX_SZ;       // [MT1*8][LDJ]   Jacobians, later [NE][NPE][3] tractions
+    double* XXs = smem;                 // 2 x [KS1*4][LDX] nodal coordinates (double buffer), rows >= NPE stay zero
+    double* Scr = XXs + 2 * S::XX_SZ;   // [MT1*8][LDJ]   Jacobians, later [NE][NPE][3] tractions
     double* Ps = Scr + S::SCR_SZ;       // [KS3*4][LDP]   P, rows >= 3 NG stay zero
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lr = lane >> 2, lc = lane & 3;  // fragment row group / thread-in-group
@@ -69,50 +71,77 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
             const int g = r / 3, k = r - 3 * g;
             A3[j][ks] = (a < NPE && r < S::K3) ? jm[(k * NPE + a) * ldg + g] : 0.0;
         }
-    for (int i = threadIdx.x; i < S::XX_SZ; i += MMA_THREADS) XXs[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * S::XX_SZ; i += MMA_THREADS) XXs[i] = 0.0;
     for (int i = threadIdx.x; i < S::P_SZ; i += MMA_THREADS) Ps[i] = 0.0;
 
-    const int64_t nbatch = (nelem + NE - 1) / NE;
-    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-        const int64_t e0 = batch * NE;
-        const int ne = (int)min((int64_t)NE, nelem - e0);
-        __syncthreads();
-        // gather [X | x] of the batch: XXs[a][e*6 + c]
-        for (int it = threadIdx.x; it < NE * NPE; it += MMA_THREADS) {
-            const int el = it / NPE, a = it - el * NPE;
-            double v[6] = {0, 0, 0, 0, 0, 0};
-            if (el < ne) {
-                const int64_t n = conn[e0 * NPE + it];
+    // Asynchronous gather (cp.async, 8 bytes per coordinate) of the [X | x] tile of a batch into buffer `buf`:
+    // XX[a][e*6 + c].  Elements beyond the end of the mesh are zero-filled.
+    auto gather = [&](int64_t b0, int buf) {
+        double* dstb = XXs + buf * S::XX_SZ;
+        const int nb = (int)min((int64_t)NE, nelem - b0);
 #pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    v[l] = X[n * 3 + l];
-                    v[3 + l] = x[n * 3 + l];
+        for (int q = 0; q < GI; ++q) {
+            const int it = threadIdx.x + q * MMA_THREADS;
+            if (it < NE * NPE) {
+                const int el = it / NPE, a = it - el * NPE;
+                double* d = dstb + a * S::LDX + el * 6;
+                if (el < nb) {
+                    const int64_t n = conn[b0 * NPE + it];
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8 * l), "l"(X + n * 3 + l));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8 * (3 + l)), "l"(x + n * 3 + l));
+                    }
+                } else {
+#pragma unroll
+                    for (int l = 0; l < 6; ++l) d[l] = 0.0;
                 }
             }
-#pragma unroll
-            for (int l = 0; l < 6; ++l) XXs[a * S::LDX + el * 6 + l] = v[l];
         }
-        __syncthreads();
-        // ---- GEMM 1: Jacobians
+        asm volatile("cp.async.commit_group;");
+    };
+
+    const int64_t nbatch = (nelem + NE - 1) / NE;
+    __syncthreads();
+    if ((int64_t)blockIdx.x < nbatch) gather((int64_t)blockIdx.x * NE, 0);
+    int buf = 0;
+    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x, buf ^= 1) {
+        const int64_t e0 = batch * NE;
+        const int ne = (int)min((int64_t)NE, nelem - e0);
+        const double* XXc = XXs + buf * S::XX_SZ;
+        asm volatile("cp.async.wait_all;");
+        __syncthreads();   // coordinates of this batch have landed; previous batch's write-out is finished
+        // prefetch the next batch while this one is computed
+        if (batch + gridDim.x < nbatch) gather((batch + gridDim.x) * NE, buf ^ 1);
+        // ---- GEMM 1: Jacobians.  NB1 n-tiles are accumulated together so MTW1*NB1 independent DMMA chains are in flight.
 #pragma unroll 1
-        for (int jn = 0; jn < NTW1; ++jn) {
-            const int nt = wn1 + WN1 * jn;
-            double c[MTW1][2];
+        for (int jn = 0; jn < NTW1; jn += NB1) {
+            double c[MTW1][NB1][2];
 #pragma unroll
-            for (int j = 0; j < MTW1; ++j) c[j][0] = c[j][1] = 0.0;
+            for (int j = 0; j < MTW1; ++j)
+#pragma unroll
+                for (int q = 0; q < NB1; ++q) c[j][q][0] = c[j][q][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < S::KS1; ++ks) {
-                const double b = XXs[(4 * ks + lc) * S::LDX + 8 * nt + lr];
+                double b[NB1];
 #pragma unroll
-                for (int j = 0; j < MTW1; ++j) dmma884(c[j][0], c[j][1], A1[j][ks], b);
+                for (int q = 0; q < NB1; ++q) b[q] = XXc[(4 * ks + lc) * S::LDX + 8 * (wn1 + WN1 * (jn + q)) + lr];
+#pragma unroll
+                for (int j = 0; j < MTW1; ++j)
+#pragma unroll
+                    for (int q = 0; q < NB1; ++q) dmma884(c[j][q][0], c[j][q][1], A1[j][ks], b[q]);
             }
 #pragma unroll
             for (int j = 0; j < MTW1; ++j) {
                 const int mt = wm1 + WM1 * j;
                 if (mt < S::MT1) {
-                    double* o = Scr + (8 * mt + lr) * S::LDJ + 8 * nt + 2 * lc;
-                    o[0] = c[j][0];
-                    o[1] = c[j][1];
+#pragma unroll
+                    for (int q = 0; q < NB1; ++q) {
+                        double* o = Scr + (8 * mt + lr) * S::LDJ + 8 * (wn1 + WN1 * (jn + q)) + 2 * lc;
+                        o[0] = c[j][q][0];
+                        o[1] = c[j][q][1];
+                    }
                 }
             }
         }
@@ -162,29 +191,36 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
                 for (int i = 0; i < 3; ++i) Ps[(g * 3 + k) * S::LDP + el * 3 + i] = Pv[k * 3 + i];
         }
         __syncthreads();
-        // ---- GEMM 2: nodal tractions, staged in shared memory in te layout [e][a][i]
-#pragma unroll 1
-        for (int jn = 0; jn < NTW3; ++jn) {
-            const int nt = wn3 + WN3 * jn;
-            double c[MTW3][2];
+        // ---- GEMM 2: nodal tractions, staged in shared memory in te layout [e][a][i].  All n-tiles of the warp and two
+        // K halves are accumulated together (MTW3*NTW3*2 independent DMMA chains).
+        {
+            double c[MTW3][NTW3][2][2];
 #pragma unroll
-            for (int j = 0; j < MTW3; ++j) c[j][0] = c[j][1] = 0.0;
+            for (int j = 0; j < MTW3; ++j)
+#pragma unroll
+                for (int q = 0; q < NTW3; ++q) c[j][q][0][0] = c[j][q][0][1] = c[j][q][1][0] = c[j][q][1][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < S::KS3; ++ks) {
-                const double b = Ps[(4 * ks + lc) * S::LDP + 8 * nt + lr];
+                double b[NTW3];
 #pragma unroll
-                for (int j = 0; j < MTW3; ++j) dmma884(c[j][0], c[j][1], A3[j][ks], b);
+                for (int q = 0; q < NTW3; ++q) b[q] = Ps[(4 * ks + lc) * S::LDP + 8 * (wn3 + WN3 * q) + lr];
+#pragma unroll
+                for (int j = 0; j < MTW3; ++j)
+#pragma unroll
+                    for (int q = 0; q < NTW3; ++q) dmma884(c[j][q][ks & 1][0], c[j][q][ks & 1][1], A3[j][ks], b[q]);
             }
 #pragma unroll
             for (int j = 0; j < MTW3; ++j) {
                 const int a = 8 * (wm3 + WM3 * j) + lr;
                 if (a < NPE) {
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int n = 8 * nt + 2 * lc + q;
-                        const int el = n / 3, i = n - 3 * el;
-                        Scr[el * (NPE * 3) + a * 3 + i] = c[j][q];
-                    }
+                    for (int q = 0; q < NTW3; ++q)
+#pragma unroll
+                        for (int z = 0; z < 2; ++z) {
+                            const int n = 8 * (wn3 + WN3 * q) + 2 * lc + z;
+                            const int el = n / 3, i = n - 3 * el;
+                            Scr[el * (NPE * 3) + a * 3 + i] = c[j][q][0][z] + c[j][q][1][z];
+                        }
                 }
             }
         }
