@@ -58,7 +58,7 @@ class Clocks(object):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -85,6 +85,9 @@ class Clocks(object):
             if len(f) < 7:
                 continue
             try:
+                if float(f[2]) < 250.0:   # idle sample (power draw in W), not part of the load
+                    mx.append(float(f[1]))
+                    continue
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
@@ -134,7 +137,7 @@ def run_reference(args, rank, world):
     n = args.n
     # bounded sample: a slab of the same mesh, ~cores * 30k elements per step
     per_core = 30000
-    nz = max(1, min(n, int(round(cores * per_core / (6.0 * n * n)))))
+    nz = max(1, min(n, int(round(min(cores * per_core, 400000) / (6.0 * n * n)))))
     pts, els = flmesh.box_tet_mesh(n, n, nz, p=2, lengths=(1.0, 1.0, float(nz) / n))
     pts, els = pts.numpy(), els.numpy().astype(np.uint64)
     Bases, Jm, AG = flmesh.tables("tet", 2)
@@ -217,12 +220,13 @@ def run_b200(args, rank, world, local_rank):
     V = torch.empty(nnz, dtype=torch.float64, device=dev)
     T = torch.empty(nnode * 3, dtype=torch.float64, device=dev)
     ndof = 30
-    for _ in range(max(args.warmup, 3)):
-        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
-    barrier()
     clocks = Clocks(local_rank)
     if rank == 0:
         clocks.start()
+        time.sleep(1.0)   # nvidia-smi needs about a second before its first sample
+    for _ in range(max(args.warmup, 3)):
+        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -242,6 +246,14 @@ def run_b200(args, rank, world, local_rank):
         kms.append(h.get_timing())
     h.set_timing(False)
     launches += 3 * args.steps
+    # hold the same load for ~0.5 s so the 20 ms nvidia-smi sampler sees the clocks the timed region ran at
+    t_hold = time.perf_counter()
+    nhold = 0
+    while time.perf_counter() - t_hold < 0.5:
+        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+        torch.cuda.synchronize()
+        nhold += 1
+    launches += 3 * nhold
     clk = clocks.stop() if rank == 0 else None
     kms = np.array(kms)
     k_elem, k_csr, k_T = kms.mean(0)
