@@ -1,0 +1,108 @@
+"""GPU: BASELINE.json's full-size configs, checked through size-independent properties (the oracle cannot run these sizes in
+seconds): rigid-body null space, symmetry, equilibrium of internal forces, translation invariance, COO/CSR checksum,
+run-to-run bit reproducibility, and agreement with the oracle on a random sample of elements."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_tet10_linear_elastic_1M_elements():
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    dev = torch.device("cuda:0")
+    n = 55
+    pts, els = flmesh.box_tet_mesh(n, n, n, p=2, device=dev)
+    assert els.shape == (998250, 10) and pts.shape == (1367631, 3)
+    Bases, Jm, AG = flmesh.tables("tet", 2)
+    x = flmesh.perturbed_state(pts, 1.0 / n, 1e-3 * n, seed=0)
+    mu, lamb = 1.0e5, 1.5e5
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases, device=dev)
+    mat = backend.make_material(10, 0.0, mu=mu, lamb=lamb)
+    indices, indptr = h.sparsity_pattern(3)
+    nrow = 3 * pts.shape[0]
+    assert indptr[-1].item() == indices.numel() and indices.numel() == h.nnz[3]
+    # pattern: sorted, duplicate-free rows, diagonal present
+    rowlen = (indptr[1:] - indptr[:-1]).long()
+    assert int(rowlen.min()) > 0
+    d = indices[1:] - indices[:-1]
+    starts = torch.zeros(indices.numel(), dtype=torch.bool, device=dev)
+    starts[indptr[1:-1].long()] = True
+    assert bool((d[~starts[1:]] > 0).all())
+    V, T = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+    V2, T2 = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+    assert torch.equal(V, V2) and torch.equal(T, T2)            # deterministic reduction
+    K = torch.sparse_csr_tensor(indptr.long(), indices.long(), V, size=(nrow, nrow))
+    scale = float(V.abs().max())
+    # rigid translations are in the null space of K (row sums of each displacement component vanish)
+    for c in range(3):
+        r = torch.zeros(nrow, dtype=torch.float64, device=dev)
+        r[c::3] = 1.0
+        assert float((K @ r).abs().max()) <= 1e-9 * scale
+    # symmetry: y^T K z == z^T K y for random vectors
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    y = torch.rand(nrow, dtype=torch.float64, device=dev, generator=g)
+    z = torch.rand(nrow, dtype=torch.float64, device=dev, generator=g)
+    a, b = float(y @ (K @ z)), float(z @ (K @ y))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    # internal forces are self-equilibrated
+    assert float(T.view(-1, 3).sum(0).abs().max()) <= 1e-9 * float(T.abs().max()) * 1e3
+    # COO mode carries the same matrix: checksum of checksums, and T is identical
+    I, J, Vc, Tc = h.assemble_implicit(x, None, mat, 0, True, mode="coo")
+    assert torch.equal(Tc, T)
+    assert abs(float(Vc.sum()) - float(V.sum())) <= 1e-9 * scale
+    w = torch.rand(nrow, dtype=torch.float64, device=dev, generator=g)
+    lhs = float((w[I.long()] * Vc * z[J.long()]).sum())
+    rhs = float(w @ (K @ z))
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+    # a random sample of element matrices against the oracle (COO layout is element-major)
+    rng = np.random.default_rng(0)
+    sample = np.sort(rng.choice(els.shape[0], 64, replace=False))
+    P, X = pts.cpu().numpy(), x.cpu().numpy()
+    E = els[torch.as_tensor(sample, device=dev)].cpu().numpy()
+    Io, Jo, Vo, To = orc.assemble_implicit(P, E, X, None, Jm, AG, 3, 6, 1, orc.params(mu=mu, lamb=lamb), 10, mode="coo")
+    Vs = Vc.view(-1, 900)[torch.as_tensor(sample, device=dev)].reshape(-1).cpu().numpy()
+    assert np.abs(Vs - Vo).max() <= 1e-10 * np.abs(Vo).max()
+    h.close()
+
+
+def test_config3_hex27_neohookean_explicit_8M_elements():
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    dev = torch.device("cuda:0")
+    n = 200
+    pts, els = flmesh.box_hex_mesh(n, n, n, p=2, device=dev)
+    assert els.shape == (8000000, 27)
+    Bases, Jm, AG = flmesh.tables("hex", 2)
+    x = flmesh.perturbed_state(pts, 0.5 / n, 0.02, seed=0)
+    mu, lamb = 4.0e5, 2.0e6
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases, device=dev)
+    mat = backend.make_material(1, 1100.0, mu=mu, lamb=lamb)
+    T = h.assemble_explicit(x, None, mat, 0)
+    assert torch.equal(T, h.assemble_explicit(x, None, mat, 0))
+    Tmax = float(T.abs().max())
+    assert float(T.view(-1, 3).sum(0).abs().max()) <= 1e-8 * Tmax * 1e3          # self-equilibrated
+    shift = torch.tensor([0.25, -0.5, 0.125], dtype=torch.float64, device=dev)   # exactly representable translation
+    Ts = h.assemble_explicit(x + shift, None, mat, 0)
+    assert float((Ts - T).abs().max()) <= 1e-9 * Tmax
+    T0 = h.assemble_explicit(pts, None, mat, 0)                                   # undeformed: F = I -> sigma = 0
+    assert float(T0.abs().max()) <= 1e-9 * Tmax
+    # scalar kernel and tensor-core kernel agree
+    h.set_option(0, 0)
+    Tsc = h.assemble_explicit(x, None, mat, 0)
+    h.set_option(0, 1)
+    assert float((Tsc - T).abs().max()) <= 1e-11 * Tmax
+    # nodes whose whole element patch lies inside a sampled slab: compare with the oracle there
+    k0 = 3
+    sel = torch.arange(k0 * n * n, (k0 + 3) * n * n, device=dev)[:: 997][:40]
+    E = els[sel].cpu().numpy()
+    nodes = np.unique(E)
+    remap = -np.ones(pts.shape[0], dtype=np.int64); remap[nodes] = np.arange(nodes.size)
+    P, X = pts[torch.as_tensor(nodes, device=dev)].cpu().numpy(), x[torch.as_tensor(nodes, device=dev)].cpu().numpy()
+    # per-element tractions: assemble each sampled element alone on both sides
+    hs = backend.AssemblyHandle(P, remap[E], Jm, AG, Bases, device=dev)
+    Tl = hs.assemble_explicit(X, None, mat, 0).cpu().numpy()
+    To = orc.assemble_explicit(P, remap[E], X, None, Jm, AG, 3, orc.params(mu=mu, lamb=lamb), 1)
+    assert np.linalg.norm(Tl - To) <= 1e-11 * np.linalg.norm(To)
+    hs.close(); h.close()
