@@ -292,3 +292,58 @@ def install(florence_module=None):
             setattr(asm, name, globals()[name])
     target.has_low_level_dispatcher = True
     return target
+
+
+# ------------------------------------------------------------------------------------------------ a1 / a2: the callers
+def LowLevelAssembly(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """Assembly.py:37-95: dispatch on formulation.fields, one-off mass for dynamic analyses, returns (K, T[:,None], F, M)."""
+    from time import time
+    t_assembly = time()
+    if not getattr(material, "has_low_level_dispatcher", True):
+        raise RuntimeError("Cannot dispatch to low level module since material {} does not support it".format(type(material).__name__))
+    if formulation.fields == "electrostatics":
+        stiffness, T = _LowLevelAssemblyLaplacian_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+        fem_solver.assembly_time = time() - t_assembly
+        return stiffness, T[:, None], None, None
+    M = []
+    if getattr(fem_solver, "analysis_type", "static") != "static" and getattr(fem_solver, "is_mass_computed", True) is False:
+        M = _mass_for(fem_solver, function_space, formulation, mesh, material)
+        fem_solver.is_mass_computed = True
+    stiffness, T, F, _ = _LowLevelAssembly_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+    fem_solver.assembly_time = time() - t_assembly
+    return stiffness, T[:, None], F, M
+
+
+def Assemble(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """Assembly.py:25-34 with has_low_level_dispatcher=True (this back end has no other path)."""
+    return LowLevelAssembly(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+
+
+def _mass_for(fem_solver, function_space, formulation, mesh, material):
+    mass_type = getattr(fem_solver, "mass_type", "lumped")
+    if fem_solver.recompute_sparsity_pattern:
+        out = __TotalConstantMassIntegrand__(mesh, function_space, formulation, mass_type, rho=material.rho)
+        M = out[0]
+        if mass_type == "consistent":
+            n = formulation.nvar * mesh.points.shape[0]
+            M = csr_matrix((out[3], (out[1], out[2])), shape=(n, n), dtype=np.float64)
+        return M
+    out = __TotalConstantMassIntegrand__(mesh, function_space, formulation, mass_type, False, fem_solver.squeeze_sparsity_pattern,
+                                         fem_solver.indices, fem_solver.indptr, rho=material.rho)
+    M = out[0]
+    if mass_type == "consistent":
+        n = formulation.nvar * mesh.points.shape[0]
+        M = csr_matrix((out[1], fem_solver.indices, fem_solver.indptr), shape=(n, n), dtype=np.float64)
+    return M
+
+
+def AssembleExplicit(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
+    """Assembly.py:664-715: (T[:,None], F, M); the first call also builds the (lumped or consistent) mass."""
+    if not getattr(material, "has_low_level_dispatcher", True):
+        raise RuntimeError("Cannot dispatch to low level module, since material {} does not support it".format(type(material).__name__))
+    T, F, M = _LowLevelAssemblyExplicit_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+    if getattr(fem_solver, "is_mass_computed", True) is True:
+        return T[:, None], F, M
+    M = _mass_for(fem_solver, function_space, formulation, mesh, material)
+    fem_solver.is_mass_computed = True
+    return T[:, None], [], M

@@ -131,3 +131,49 @@ def device_pack_functions(handle):
         check(lib.fl_unpack_add_nodes(C.c_void_p(T.data_ptr()), C.c_void_p(ids.data_ptr()), ids.numel(), buf.numel() // ids.numel(),
                                       C.c_void_p(buf.data_ptr()), _s()))
     return pack, unpack_add
+
+
+# ------------------------------------------------------------------------------------------------ implicit: owned CSR row blocks
+class RowPartition(Partition):
+    """Partition for implicit assembly: the local mesh holds every element that touches a node owned by this rank (the rank's
+    block plus halo elements), so the CSR rows of owned nodes are complete without any communication
+    ("each rank emits the CSR row block it owns")."""
+
+    def __init__(self, rank, world, points, elements, node_map, owned_local, n_halo_elements):
+        Partition.__init__(self, rank, world, points, elements, node_map, {})
+        self.owned_local = owned_local            # local node ids owned by this rank (ascending global id)
+        self.n_halo_elements = n_halo_elements
+
+    def owned_rows(self, V, indices, indptr, nvar):
+        """Slice the locally assembled CSR (V, indices, indptr over local dofs) down to the owned rows and translate the
+        column indices to GLOBAL dof numbers.  Returns (global_row_ids, indptr_block, global_cols, values)."""
+        V, indices, indptr = np.asarray(V), np.asarray(indices), np.asarray(indptr)
+        gl = np.asarray(self.node_map)
+        rows_local = (np.asarray(self.owned_local)[:, None] * nvar + np.arange(nvar)[None, :]).ravel()
+        starts, ends = indptr[rows_local], indptr[rows_local + 1]
+        counts = ends - starts
+        take = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if rows_local.size else np.zeros(0, np.int64)
+        cols_local = indices[take]
+        cols_global = gl[cols_local // nvar] * nvar + cols_local % nvar
+        rows_global = (gl[np.asarray(self.owned_local)][:, None] * nvar + np.arange(nvar)[None, :]).ravel()
+        return rows_global, np.concatenate([[0], np.cumsum(counts)]), cols_global, V[take]
+
+
+def row_partition(points, elements, rank, world):
+    """Node ownership = lowest rank whose contiguous element block (np.array_split, Mesh.py:7403) contains the node;
+    local elements = every element with at least one owned node."""
+    pts = np.asarray(points)
+    els = np.asarray(elements).astype(np.int64)
+    blocks = element_blocks(els.shape[0], world)
+    owner = np.full(pts.shape[0], world, dtype=np.int64)
+    for r in range(world - 1, -1, -1):
+        owner[np.unique(els[blocks[r][0]:blocks[r][1]])] = r
+    touches = (owner[els] == rank).any(axis=1)
+    local_els = els[touches]
+    b0, b1 = blocks[rank]
+    n_halo = int(touches.sum() - touches[b0:b1].sum())
+    nodes = np.unique(local_els)
+    local = np.searchsorted(nodes, local_els)
+    owned_local = np.nonzero(owner[nodes] == rank)[0]
+    return RowPartition(rank, world, torch.as_tensor(pts[nodes]), torch.as_tensor(local), torch.as_tensor(nodes),
+                        torch.as_tensor(owned_local), n_halo)

@@ -88,3 +88,75 @@ class ExplicitStructuralDynamicIntegrator(object):
                 print("Explicit solver blew up! Norm of incremental solution is too large")
                 break
         return snaps
+
+
+    # -------------------------------------------------------------------------------------------- reference signature
+    @classmethod
+    def Solver(cls, function_spaces, formulation, solver, TractionForces, M, NeumannForces, NodalForces, Residual, mesh, TotalDisp,
+               Eulerx, Eulerp, material, boundary_condition, fem_solver):
+        """Drop-in for ExplicitStructuralDynamicIntegrator.Solver (ExplicitStructuralDynamicIntegrator.py:28-244), mechanics with
+        lumped mass.  Same arguments; returns TotalDisp (nnode x nvar x nincrements) with the reference's save rules.
+        The loop runs on the device; per increment the host only selects the load / Dirichlet columns."""
+        from . import assembly
+        if formulation.fields != "mechanics":
+            raise NotImplementedError("Explicit solver for {} is not available on this back end".format(formulation.fields))
+        if getattr(fem_solver, "mass_type", "lumped") != "lumped":
+            raise NotImplementedError("Only lumped mass is supported by the device-resident explicit loop")
+        if getattr(fem_solver, "include_physical_damping", False):
+            raise NotImplementedError("Damping is not included in the explicit solver")
+        fspace = function_spaces[1] if len(function_spaces) > 1 else function_spaces[0]
+        h = assembly.get_handle(mesh, fspace)
+        mat = assembly._material_struct(material)
+        dev = h.device
+        ndim, nnode = formulation.ndim, mesh.points.shape[0]
+        LoadIncrement = fem_solver.number_of_load_increments
+        dt = fem_solver.total_time / LoadIncrement
+        self = cls(h, mat, M=np.asarray(M, dtype=np.float64).ravel())
+        NeumannForces = np.asarray(NeumannForces, dtype=np.float64)
+        if NeumannForces.ndim == 1:
+            NeumannForces = NeumannForces[:, None]
+        fixed = np.zeros(nnode * ndim, dtype=np.uint8)
+        fixed[np.asarray(boundary_condition.columns_out)] = 1
+        self.X = backend.to_device(mesh.points, torch.float64, dev).reshape(-1)
+        self.fixed = backend.to_device(fixed, torch.uint8, dev)
+        self.Eulerx = backend.to_device(Eulerx, torch.float64, dev).reshape(-1).clone()
+        self.T = backend.to_device(np.asarray(TractionForces, dtype=np.float64).ravel(), torch.float64, dev).clone()
+        # start-up, :57-81 (zero initial displacement and velocity)
+        A0 = (backend.to_device(np.ascontiguousarray(NeumannForces[:, 0]), torch.float64, dev) - self.T) / self.M
+        self.U0 = torch.zeros_like(self.T)
+        self.U00 = (dt ** 2 / 2.) * A0
+        self.U00[self.fixed.bool()] = 0.0
+        self.dt = dt
+        TotalDisp[:, :ndim, 0] = self.U00.view(nnode, ndim).cpu().numpy()
+        save_frequency = getattr(fem_solver, "save_frequency", 1)
+        save_counter = 2 if save_frequency == 1 else 1
+        nincr_last = float(LoadIncrement - 1) if LoadIncrement != 1 else 1
+        applied = np.asarray(boundary_condition.applied_dirichlet, dtype=np.float64)
+        cols_out = torch.as_tensor(np.asarray(boundary_condition.columns_out).astype(np.int64), device=dev)
+        incd = torch.zeros_like(self.T)
+        ramp = getattr(boundary_condition, "make_loading", "ramp") == "ramp"
+        for Increment in range(2, LoadIncrement):
+            # incremental Dirichlet / Neumann data, :101-128
+            if applied.ndim == 2:
+                inc_col = applied[:, Increment - 1]
+            else:
+                inc_col = applied * (1. * Increment / LoadIncrement) if ramp else applied / nincr_last
+            incd.zero_()
+            incd[cols_out] = backend.to_device(np.ascontiguousarray(inc_col), torch.float64, dev)
+            if NeumannForces.shape[1] > 1:
+                fext = backend.to_device(np.ascontiguousarray(NeumannForces[:, Increment - 1]), torch.float64, dev)
+            else:
+                fext = backend.to_device(NeumannForces.ravel() * ((1. * Increment / LoadIncrement) if ramp else 1.0 / nincr_last), torch.float64, dev)
+            status = h.explicit_steps(mat, dt, 1, Increment, self.M, fext, self.fixed, incd, self.U0, self.U00, self.Eulerx, self.T,
+                                      fext_scale0=1.0, fext_scale_step=0.0)
+            if Increment % save_frequency == 0 or (Increment == LoadIncrement - 1 and save_counter < TotalDisp.shape[2]):
+                TotalDisp[:, :ndim, save_counter] = (self.Eulerx - self.X).view(nnode, ndim).cpu().numpy()
+                save_counter += 1
+            if status:
+                print("Explicit solver blew up! Norm of incremental solution is too large")
+                TotalDisp = TotalDisp[:, :, :Increment]
+                fem_solver.number_of_load_increments = Increment
+                break
+        if isinstance(Eulerx, np.ndarray):
+            Eulerx[:, :] = self.Eulerx.view(nnode, ndim).cpu().numpy()
+        return TotalDisp

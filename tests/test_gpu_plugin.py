@@ -110,3 +110,35 @@ def test_unknown_material_and_laplacian_dispatch():
         with pytest.raises(ValueError):
             assembly._LowLevelAssemblyLaplacian_(so, fs, fo, me, mat, pts, np.zeros(me.nnode))
     assembly.clear_handles()
+
+
+def test_explicit_integrator_solver_signature_reproduces_reference_trajectory():
+    """ExplicitStructuralDynamicIntegrator.Solver with the reference's argument list, fed with what FEMSolver.Solve hands it
+    (recorded in the fixture), must reproduce the TotalDisp the reference's own integrator produced."""
+    from florence_b200 import assembly
+    from florence_b200.time_integrator import ExplicitStructuralDynamicIntegrator as ESDI
+    g = np.load(os.path.join(GOLD, "golden_explicit.npz"))
+    pts, els = g["exp_points"], g["exp_elements"].astype(np.uint64)
+    fs, fo, me, so, bc, mat = Obj(), Obj(), Obj(), Obj(), Obj(), type("NeoHookean", (object,), {})()
+    fs.Bases, fs.Jm, fs.AllGauss = g["exp_Bases"], g["exp_Jm"], g["exp_AllGauss"]
+    fo.ndim, fo.nvar, fo.fields = 3, 3, "mechanics"
+    me.points, me.elements, me.nelem = pts, els, els.shape[0]
+    me.ChangeType = lambda: None
+    nsteps = int(g["exp_nsteps"])
+    so.number_of_load_increments, so.total_time, so.mass_type, so.save_frequency = nsteps, float(g["exp_dt"]) * nsteps, "lumped", 1
+    so.include_physical_damping, so.is_mass_computed, so.recompute_sparsity_pattern = False, False, True
+    bc.columns_out, bc.applied_dirichlet, bc.make_loading = g["exp_columns_out"], g["exp_applied_dirichlet"], "ramp"
+    prm = g["exp_prm"]
+    mat.mu, mat.lamb, mat.rho, mat.mtype = float(prm[0]), float(prm[5]), float(g["exp_rho"]), "NeoHookean"
+    # AssembleExplicit's first call: T of the undeformed mesh and the lumped mass (Assembly.py:664-715)
+    T0, _, M = assembly.AssembleExplicit(so, fs, fo, me, mat, pts.copy(), np.zeros(pts.shape[0]))
+    assert so.is_mass_computed is True
+    assert np.abs(M.ravel() - g["exp_M_lumped"]).max() <= 1e-12 * np.abs(g["exp_M_lumped"]).max()
+    TotalDisp = np.zeros((pts.shape[0], 3, nsteps))
+    Eulerx = pts.copy()
+    out = ESDI.Solver([fs, fs], fo, None, T0, M, g["exp_neumann"], None, None, me, TotalDisp, Eulerx, np.zeros(pts.shape[0]), mat, bc, so)
+    ref = g["exp_TotalDisp"]
+    assert out.shape == ref.shape
+    for inc in range(2, nsteps):
+        assert np.abs(out[:, :, inc] - ref[:, :, inc]).max() <= 1e-10 * np.abs(ref).max(), inc
+    assembly.clear_handles()

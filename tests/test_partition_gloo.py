@@ -78,3 +78,61 @@ def test_partition_and_interface_exchange(kind, world):
         assert errT < 1e-13 and errM < 1e-13, (rank, errT, errM)
         assert ok_blocks
         assert nshared > 0
+
+
+def _row_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from scipy.sparse import csr_matrix
+        pts, els = flmesh.box_tet_mesh(3, 3, 4, p=2)
+        Bases, Jm, AG = flmesh.tables("tet", 2)
+        P, E = pts.numpy(), els.numpy()
+        X = P + 0.01 * np.sin(5.0 * P + 0.1)
+        prm = orc.params(mu=1e5, lamb=1.5e5)
+        part = partition.row_partition(P, E, rank, world)
+        gl = part.node_map.numpy()
+        lp, le = part.points.numpy(), part.elements.numpy()
+        pat = orc.sparsity_pattern(le, lp.shape[0], 3)
+        V, T = orc.assemble_implicit(lp, le, X[gl], None, Jm, AG, 3, 6, 1, prm, 10, mode="csr", pattern=pat)
+        rows, iptr, cols, vals = part.owned_rows(V, pat[0], pat[1], 3)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (rows, iptr, cols, vals, T.reshape(-1, 3)[part.owned_local.numpy()], gl[part.owned_local.numpy()]))
+        if rank == 0:
+            n = 3 * P.shape[0]
+            patg = orc.sparsity_pattern(E, P.shape[0], 3)
+            Vg, Tg = orc.assemble_implicit(P, E, X, None, Jm, AG, 3, 6, 1, prm, 10, mode="csr", pattern=patg)
+            Kg = csr_matrix((Vg, patg[0], patg[1]), shape=(n, n))
+            allrows = np.concatenate([g[0] for g in gathered])
+            ok_cover = np.array_equal(np.sort(allrows), np.arange(n))         # every row owned exactly once
+            err = 0.0
+            errT = 0.0
+            for rws, ip, cl, vl, Tl, own in gathered:
+                for k, r in enumerate(rws):
+                    ref_cols = Kg.indices[Kg.indptr[r]:Kg.indptr[r + 1]]
+                    ref_vals = Kg.data[Kg.indptr[r]:Kg.indptr[r + 1]]
+                    c, v = cl[ip[k]:ip[k + 1]], vl[ip[k]:ip[k + 1]]
+                    if not np.array_equal(c, ref_cols):
+                        err = np.inf
+                        break
+                    err = max(err, np.abs(v - ref_vals).max())
+                errT = max(errT, np.abs(Tl - Tg.reshape(-1, 3)[own]).max())
+            q.put((bool(ok_cover), float(err / np.abs(Vg).max()), float(errT / np.abs(Tg).max()), int(part.n_halo_elements)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_owned_csr_row_blocks_need_no_communication(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_row_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok_cover, err, errT, n_halo = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok_cover and err < 1e-13 and errT < 1e-13 and n_halo > 0
