@@ -35,6 +35,13 @@ __global__ void narrow_conn_kernel(const uint64_t* __restrict__ in, int64_t n, i
     out[i] = (int32_t)v;
 }
 
+__global__ void transpose_jm_kernel(const double* __restrict__ in, int D, int npe, int ng, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * npe * ng) return;
+    const int g = i / (D * npe), r = i - g * D * npe, k = r / npe, a = r - k * npe;
+    out[i] = in[(k * npe + a) * ng + g];
+}
+
 __global__ void pad_jm_kernel(const double* __restrict__ in, int rows, int ng, int ldg, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * ldg) return;
@@ -117,6 +124,7 @@ int fl_create(const fl_mesh_desc* m, fl_handle** out) {
     FL_TRY(cudaMalloc(&h->conn, sizeof(int32_t) * (nk > 0 ? nk : 1)));
     FL_TRY(cudaMalloc(&h->points, sizeof(double) * h->nnode * h->ndim));
     FL_TRY(cudaMalloc(&h->jm, sizeof(double) * h->ndim * h->npe * h->ldg));
+    FL_TRY(cudaMalloc(&h->jmT, sizeof(double) * h->ndim * h->npe * h->ng));
     FL_TRY(cudaMalloc(&h->bases, sizeof(double) * h->npe * h->ng));
     FL_TRY(cudaMalloc(&h->gw, sizeof(double) * h->ng));
     FL_TRY(cudaMalloc(&h->flag, sizeof(int32_t)));
@@ -128,6 +136,8 @@ int fl_create(const fl_mesh_desc* m, fl_handle** out) {
     {
         const int tot = h->ndim * h->npe * h->ldg;
         pad_jm_kernel<<<(tot + 255) / 256, 256>>>(m->Jm, h->ndim * h->npe, h->ng, h->ldg, h->jm);
+        const int tot2 = h->ndim * h->npe * h->ng;
+        transpose_jm_kernel<<<(tot2 + 255) / 256, 256>>>(m->Jm, h->ndim, h->npe, h->ng, h->jmT);
     }
     if (nk > 0) {
         narrow_conn_kernel<<<(unsigned)((nk + 255) / 256), 256>>>(m->elements, nk, h->nnode, h->conn, h->flag);
@@ -151,6 +161,7 @@ static inline void mark(fl_handle* h, int k, cudaStream_t st) {
 int fl_set_option(fl_handle* h, int option, int value) {
     if (!h) { set_error("null handle"); return FL_ERR_INVALID; }
     if (option == 0) { h->use_mma = value ? 1 : 0; return FL_OK; }
+    if (option == 1) { h->use_mma_implicit = value; return FL_OK; }
     set_error("unknown option %d", option);
     return FL_ERR_INVALID;
 }
@@ -173,7 +184,7 @@ int fl_get_timing(fl_handle* h, float* ms) {
 int fl_destroy(fl_handle* h) {
     if (!h) return FL_OK;
     for (int k = 0; k < 4; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
-    cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->bases); cudaFree(h->gw);
+    cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->jmT); cudaFree(h->bases); cudaFree(h->gw);
     cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank);
     cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag);
     delete h;

@@ -14,7 +14,7 @@
 // geometric term on the diagonal block.  One thread owns column (b,j) of K_e for a chunk of A row nodes, so K_e rows are
 // written as contiguous (coalesced) segments and nothing is recomputed.  fp64 accumulators live in registers.
 #pragma once
-#include "fl_internal.cuh"
+#include "fl_implicit_mma.cuh"
 
 namespace fl {
 
@@ -504,6 +504,12 @@ int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, cons
 template <int D, int MAT>
 int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, const MatParams& prm, int update, double* ke, double* te,
                     cudaStream_t st) {
+    if constexpr (D == 3) {
+        // p = 3 hexahedra: dense parent-space contraction on the fp64 tensor cores (fl_implicit_mma.cuh); hex27 only when
+        // forced (option value 2): its 27 -> 32 tile padding makes the generic kernel the faster one
+        if (h->use_mma_implicit == 2 && h->npe == 27 && h->ng == 27) return launch_impl_mma<MAT, 27, 27, 21>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+        if (h->use_mma_implicit && h->npe == 64 && h->ng == 64) return launch_impl_mma<MAT, 64, 64, 12>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+    }
     const int rows = h->npe / 2 + 1;
     if (rows <= 3) return launch_impl_A<D, MAT, 3>(h, Eulerx, Eulerp, prm, update, ke, te, st);
     if (rows <= 6) return launch_impl_A<D, MAT, 6>(h, Eulerx, Eulerp, prm, update, ke, te, st);

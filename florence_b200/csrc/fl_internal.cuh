@@ -42,6 +42,7 @@ struct fl_handle {
     int32_t* conn = nullptr;     // nelem x npe
     double* points = nullptr;    // nnode x ndim
     double* jm = nullptr;        // [k][a][ldg]: Jm[k][a][g]
+    double* jmT = nullptr;       // [g][k][a]  : the same table, node index fastest
     double* bases = nullptr;     // [a][ng]
     double* gw = nullptr;        // [ng]
     // node -> flat connectivity index (e*npe+a), ascending in e: the order the reference's element loop sums in
@@ -56,7 +57,8 @@ struct fl_handle {
     int sm_count = 148;
     int max_smem_optin = 0;
     int timing = 0;
-    int use_mma = 1;             // explicit path: DMMA kernels for hex8 / hex27 (fl_set_option)
+    int use_mma = 1;             // explicit path: DMMA kernels for hex8 / hex27 (fl_set_option 0)
+    int use_mma_implicit = 1;    // implicit path: DMMA kernels for hex27 / hex64 (fl_set_option 1)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

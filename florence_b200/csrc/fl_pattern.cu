@@ -350,6 +350,59 @@ csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict
     }
 }
 
+// Wide rows (high-order elements: nvar*ndof > 128 doubles per visit): one block per node, the threads split each visit's run.
+template <int NV>
+__global__ void __launch_bounds__(256)
+csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
+                       const uint16_t* __restrict__ rank, const double* __restrict__ ke, int64_t nnode, int npe, double* __restrict__ V) {
+    extern __shared__ double rowbuf[];
+    const int ndof = npe * NV;
+    const int run = NV * ndof;
+    for (int64_t n = blockIdx.x; n < nnode; n += gridDim.x) {
+        const int w = (int)(nbr_ptr[n + 1] - nbr_ptr[n]) * NV;
+        __syncthreads();
+        for (int t = threadIdx.x; t < NV * w; t += blockDim.x) rowbuf[t] = 0.0;
+        __syncthreads();
+        const int64_t k1 = adj_ptr[n + 1];
+        for (int64_t k = adj_ptr[n]; k < k1; ++k) {
+            const int64_t flat = adj_idx[k];
+            const int64_t e = flat / npe;
+            const int a = (int)(flat - e * npe);
+            const uint16_t* rk = rank + flat * npe;
+            const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof;
+            for (int t = threadIdx.x; t < run; t += blockDim.x) {
+                const int i = t / ndof, c = t - i * ndof;
+                const int b = c / NV, l = c - b * NV;
+                rowbuf[i * w + (int)rk[b] * NV + l] += krow[t];
+            }
+            __syncthreads();
+        }
+        const int64_t base = nbr_ptr[n] * NV * NV;
+        for (int t = threadIdx.x; t < NV * w; t += blockDim.x) V[base + t] = rowbuf[t];
+    }
+}
+
+template <int NV>
+static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
+    const Pattern& p = h->pat;
+    const size_t smem = sizeof(double) * NV * (size_t)p.max_cnt * NV;
+    if (smem > (size_t)h->max_smem_optin) {
+        set_error("CSR rows of %d entries do not fit shared memory", p.max_cnt * NV);
+        return FL_ERR_UNSUPPORTED;
+    }
+    auto kern = csr_gather_wide_kernel<NV>;
+    FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    if (occ < 1) occ = 1;
+    int64_t blocks = h->nnode;
+    const int64_t cap = (int64_t)h->sm_count * occ * 8;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, 256, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, V);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
 template <int NV, int NPE>
 static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     const Pattern& p = h->pat;
@@ -377,6 +430,7 @@ static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaSt
 
 template <int NV>
 static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
+    if (NV * NV * h->npe > 128) return launch_csr_gather_wide<NV>(h, ke, V, st);
     switch (h->npe) {
         case 4: return launch_csr_gather_T<NV, 4>(h, ke, V, st);
         case 8: return launch_csr_gather_T<NV, 8>(h, ke, V, st);

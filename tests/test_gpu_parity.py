@@ -284,3 +284,30 @@ def test_explicit_tensor_core_kernel_equals_scalar_kernel_and_oracle(p, n):
         assert np.linalg.norm(T0 - To) <= 1e-11 * np.linalg.norm(To)
         assert np.abs(T1 - T0).max() <= 1e-11 * np.abs(To).max()
     h.close()
+
+
+@pytest.mark.parametrize("key", ["asm_hex2_n2_NeoHookean", "asm_hex3_n1_MooneyRivlin", "asm_hex2_n1_IsotropicElectroMechanics_108",
+                                 "asm_hex3_n1_IsotropicElectroMechanics_108", "asm_hex2_n1_NearlyIncompressibleMooneyRivlin"])
+def test_implicit_tensor_core_kernel_equals_generic_kernel(key):
+    """hex27 / hex64 run the DMMA parent-space formulation by default; the generic column-owner kernel must give the same K_e."""
+    from florence_b200 import backend
+    from oracle import oracle as orc
+    c = _load(key)
+    matname = key.split("_", 3)[3]
+    num = orc.MATERIAL_NUMBERS[matname]
+    form = 1 if matname in ELEC else 0
+    ndim = 3
+    nvar = ndim + form
+    h = backend.AssemblyHandle(c["points"], c["elements"], c["Jm"], c["AllGauss"], c["Bases"])
+    mat = _material(backend, num, c["prm"])
+    out = {}
+    for opt, val in ((1, 2), (0, 0)):   # 2 = force the tensor-core kernel also for hex27
+        h.set_option(1, val)
+        I, J, V, T = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, int(c["update"]), mode="coo")
+        out[opt] = (V.cpu().numpy(), T.cpu().numpy(), I.cpu().numpy(), J.cpu().numpy())
+    n = nvar * c["points"].shape[0]
+    K1 = csr_matrix((out[1][0], (out[1][2], out[1][3])), shape=(n, n))
+    K0 = csr_matrix((out[0][0], (out[0][2], out[0][3])), shape=(n, n))
+    _blockwise_close(K1, K0, nvar, ndim, 1e-10)
+    _vec_close(out[1][1], out[0][1], nvar, ndim, 1e-11)
+    h.close()
