@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--explicit-n", type=int, default=160, help="hexes per edge of the hex27 explicit line (per GPU)")
     ap.add_argument("--explicit-steps", type=int, default=20)
     ap.add_argument("--no-explicit", action="store_true")
+    ap.add_argument("--no-hiorder", action="store_true")
+    ap.add_argument("--hiorder-n", type=int, default=24, help="hexes per edge of the p=3 electro-mechanical Newton-step line (config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -383,6 +385,53 @@ def run_b200(args, rank, world, local_rank):
                             "roofline_fp64": {"achieved": Fl_x * nel / (t_el * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
                                               "frac": Fl_x * nel / (t_el * 1e-3) / 1e12 / dfma, "flops_per_element_reference_count": Fl_x}}
         hh.close()
+    # ------------------------------------------------------------------ config 4: EM_108 p=3 hex Newton-step assembly (DMMA local K)
+    if not args.no_hiorder:
+        n4 = args.hiorder_n
+        p4, e4 = flmesh.box_hex_mesh(n4, n4, n4, p=3, device=dev)
+        B4, J4, A4 = flmesh.tables("hex", 3)
+        x4 = flmesh.perturbed_state(p4, 1.0 / (3 * n4), 0.02, seed=11)
+        gen4 = torch.Generator(device=dev); gen4.manual_seed(5)
+        phi4 = 9.0e3 * p4[:, 2] + 10.0 * (2.0 * torch.rand(p4.shape[0], dtype=torch.float64, device=dev, generator=gen4) - 1.0)
+        h4 = backend.AssemblyHandle(p4, e4, J4, A4, B4, device=dev)
+        nnz4 = h4.build_pattern(4)
+        mu4 = 5.0e4
+        mat4 = backend.make_material(8, 1200.0, mu1=mu4, mu2=mu4, lamb=2.0 * mu4 * 0.4 / (1.0 - 0.8), eps_2=4.0 * 8.8541e-12)
+        V4 = torch.empty(nnz4, dtype=torch.float64, device=dev)
+        T4 = torch.empty(p4.shape[0] * 4, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            h4.assemble_implicit(x4, phi4, mat4, 1, True, mode="csr", out=(V4, T4))
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 3
+        b0.record()
+        for _ in range(nrep):
+            h4.assemble_implicit(x4, phi4, mat4, 1, True, mode="csr", out=(V4, T4))
+        b1.record()
+        torch.cuda.synchronize()
+        hms = max_over_ranks(b0.elapsed_time(b1)) / nrep
+        h4.set_timing(True)
+        h4.assemble_implicit(x4, phi4, mat4, 1, True, mode="csr", out=(V4, T4))
+        t4 = h4.get_timing()
+        h4.set_timing(False)
+        launches += 3 * (nrep + 3)
+        dmma = backend.measure_fp64_peak(True, 20000)
+        launches += 4
+        nel4 = e4.shape[0]
+        # executed tensor-core work: 16 dof pairs x (8x8 tiles) x 48 k-steps DMMAs of 256 FMAs per element
+        fl_exec = 16 * 8 * 8 * 48 * 512.0
+        line["hiorder"] = {"metric": "elements assembled/s (K+residual, fp64)", "value": nel4 * world / (hms * 1e-3), "unit": "elements/s",
+                           "ms_per_step": hms,
+                           "config": {"workload": "hex64 (p=3) IsotropicElectroMechanics_108 Newton-step K(CSR)+T, %d^3 elements per GPU" % n4,
+                                      "ndof_per_element": 256, "nnz_per_gpu": nnz4},
+                           "roofline": {"bound": "tensor", "achieved": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
+                                        "frac": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12 / dmma, "kernel": "implicit_elements_mma_kernel<EM_108,64,64,12>",
+                                        "kernel_ms": t4[0], "csr_gather_wide_ms": t4[1],
+                                        "peak_source": "measured in this run (fl_measure_fp64_peak, mma.sync.m8n8k4.f64 loop)",
+                                        "flops_per_element_executed_on_tensor_cores": fl_exec}}
+        del V4, T4
+        h4.close()
+        torch.cuda.empty_cache()
     line["gpu_launches"] = int(launches)
     if rank == 0:
         print(json.dumps(line))

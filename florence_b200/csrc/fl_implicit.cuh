@@ -60,9 +60,9 @@ struct impl_layout {
         djs = odd_stride(ng);
         size_t o = 0;
         jm_off = o; o += jm_in_smem ? (size_t)D * npe * ldg : 0;
-        X_off = o; o += (size_t)EB * xstride;
-        x_off = o; o += (size_t)EB * xstride;
-        ph_off = o; o += EL ? (size_t)EB * npe : 0;
+        X_off = o; o += (size_t)2 * EB * xstride;          // coordinates are double-buffered (cp.async prefetch of the next batch)
+        x_off = o; o += (size_t)2 * EB * xstride;
+        ph_off = o; o += EL ? (size_t)2 * EB * npe : 0;
         iJ_off = o; o += (size_t)EB * ijs;
         SG_off = o; o += (size_t)EB * sgs;
         H_off = o; o += CONST_H ? (size_t)dims::HT * dims::HT : (size_t)EB * hss;
@@ -70,6 +70,7 @@ struct impl_layout {
         dJ_off = o; o += (size_t)EB * djs;
         // K_e staging: the band mapping scatters a thread's blocks over rows, so K_e is assembled in shared memory and
         // streamed out as one contiguous run per batch
+        o += (o & 1);  // 16-byte alignment of the staging tile (vectorised write-out)
         K_off = o; o += stage ? (size_t)EB * (npe * dims::NV) * (npe * dims::NV) : 0;
         total = o;
     }
@@ -99,9 +100,9 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
     const L lay(npe, ng, ldg, EB, JM_SMEM, STAGE);
     double* Kst = smem + lay.K_off;
     double* jm_s = smem + lay.jm_off;
-    double* Xs = smem + lay.X_off;
-    double* xs = smem + lay.x_off;
-    double* ph = smem + lay.ph_off;
+    double* Xs0 = smem + lay.X_off;
+    double* xs0 = smem + lay.x_off;
+    double* ph0 = smem + lay.ph_off;
     double* iJ = smem + lay.iJ_off;   // [el][g][D*D]  J_x^-1
     double* SG = smem + lay.SG_off;   // [el][g][a][D] spatial gradients
     double* Hs = smem + lay.H_off;    // [el][g][HT*HT] hessian * detJ   (CONST_H: one unscaled copy)
@@ -131,22 +132,42 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
         }
     }
 
-    const int64_t nbatch = (nelem + EB - 1) / EB;
-    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-        const int64_t e0 = batch * EB;
-        const int ne = (int)min((int64_t)EB, nelem - e0);
-        __syncthreads();
-        for (int it = threadIdx.x; it < ne * npe; it += blockDim.x) {
+    // asynchronous gather (cp.async, 8 bytes per value) of the nodal coordinates / potentials of one batch into buffer `buf`
+    auto gather = [&](int64_t b0, int buf) {
+        const int nb = (int)min((int64_t)EB, nelem - b0);
+        double* Xb = Xs0 + buf * EB * xstride;
+        double* xb = xs0 + buf * EB * xstride;
+        double* pb = ph0 + buf * EB * npe;
+        for (int it = threadIdx.x; it < nb * npe; it += blockDim.x) {
             const int el = it / npe, a = it - el * npe;
-            const int64_t n = conn[e0 * npe + it];
+            const int64_t n = conn[b0 * npe + it];
+            const unsigned sX = (unsigned)__cvta_generic_to_shared(Xb + el * xstride + a * D);
+            const unsigned sx = (unsigned)__cvta_generic_to_shared(xb + el * xstride + a * D);
 #pragma unroll
             for (int l = 0; l < D; ++l) {
-                Xs[el * xstride + a * D + l] = X[n * D + l];
-                xs[el * xstride + a * D + l] = x[n * D + l];
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sX + 8 * l), "l"(X + n * D + l));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sx + 8 * l), "l"(x + n * D + l));
             }
-            if (EL) ph[el * npe + a] = phi[n];
+            if (EL) {
+                const unsigned sp = (unsigned)__cvta_generic_to_shared(pb + el * npe + a);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sp), "l"(phi + n));
+            }
         }
+        asm volatile("cp.async.commit_group;");
+    };
+    const int64_t nbatch = (nelem + EB - 1) / EB;
+    __syncthreads();
+    if ((int64_t)blockIdx.x < nbatch) gather((int64_t)blockIdx.x * EB, 0);
+    int buf = 0;
+    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x, buf ^= 1) {
+        const int64_t e0 = batch * EB;
+        const int ne = (int)min((int64_t)EB, nelem - e0);
+        double* Xs = Xs0 + buf * EB * xstride;
+        double* xs = xs0 + buf * EB * xstride;
+        double* ph = ph0 + buf * EB * npe;
+        asm volatile("cp.async.wait_all;");
         __syncthreads();
+        if (batch + gridDim.x < nbatch) gather((batch + gridDim.x) * EB, buf ^ 1);
         // ---- phase 1: kinematics and kinetics at (element, Gauss point)
         for (int it = threadIdx.x; it < ne * ng; it += blockDim.x) {
             const int el = it / ng, g = it - el * ng;
@@ -440,7 +461,14 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             __syncthreads();
             double* dst = ke + (size_t)e0 * ndof * ndof;
             const int tot = ne * ndof * ndof;
-            for (int t = threadIdx.x; t < tot; t += blockDim.x) dst[t] = Kst[t];
+            if ((((size_t)dst) & 15) == 0) {
+                double2* d2 = reinterpret_cast<double2*>(dst);
+                const double2* s2 = reinterpret_cast<const double2*>(Kst);
+                for (int t = threadIdx.x; t < tot / 2; t += blockDim.x) d2[t] = s2[t];
+                if ((tot & 1) && threadIdx.x == 0) dst[tot - 1] = Kst[tot - 1];
+            } else {
+                for (int t = threadIdx.x; t < tot; t += blockDim.x) dst[t] = Kst[t];
+            }
         }
     }
 }
