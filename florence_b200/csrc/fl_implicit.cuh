@@ -25,6 +25,9 @@ constexpr int IMPL_THREADS = 128;
 #ifndef FL_EB_DIV
 #define FL_EB_DIV 5
 #endif
+#ifndef FL_MINB_ISO
+#define FL_MINB_ISO 4
+#endif
 #ifndef FL_MINB_SPEC
 #define FL_MINB_SPEC 4
 #endif
@@ -516,7 +519,7 @@ int launch_impl_A(fl_handle* h, const double* Eulerx, const double* Eulerp, cons
     const size_t smem = sizeof(double) * L(npe, ng, ldg, EB, jm_in_smem, stage).total;
     // compile-time element shapes of the benchmark configs (mechanics, 3-D): tet10 (8 gp), hex8, hex27
     if constexpr (D == 3 && !EL && A == 6) {
-        if (stage && npe == 10 && ng == 8) return launch_impl_cfg<D, MAT, A, 1, 1, 10, 8, FL_MINB_SPEC, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
+        if (stage && npe == 10 && ng == 8) return launch_impl_cfg<D, MAT, A, 1, 1, 10, 8, (L::ISO ? FL_MINB_ISO : FL_MINB_SPEC), 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
         if (stage && npe == 8 && ng == 8) return launch_impl_cfg<D, MAT, A, 1, 1, 8, 8, FL_MINB_SPEC, 1>(h, Eulerx, Eulerp, prm, update, ke, te, st, EB, smem);
     }
     if constexpr (D == 3 && !EL && A == 7) {
