@@ -182,10 +182,20 @@ implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
         // ---- K^{ij} = JmT * W^{ij}: steps s = (ij, chunk).  Warps 4-7 produce W(s+1) into the other buffer while warps 0-3
         //      run the DMMAs of step s; one block barrier per step.
         double* Ke = ke + (size_t)e * ndof * ndof;
-        constexpr int NS = NV * NV * S::NCH;
+        // K is symmetric (H and the geometric term are), so only the dof pairs i <= j are contracted; K^{ji} = (K^{ij})^T is
+        // written as the mirror image.
+        constexpr int NPAIR = NV * (NV + 1) / 2;
+        constexpr int NS = NPAIR * S::NCH;
+        auto pair_ij = [](int pr, int& i, int& j) {
+            i = 0;
+            int rem = pr;
+            while (rem >= NV - i) { rem -= NV - i; ++i; }
+            j = i + rem;
+        };
         auto produce = [&](int s, int t0, int nthr) {
             const int ij = s / S::NCH, ch = s - ij * S::NCH;
-            const int i = ij / NV, j = ij - i * NV;
+            int i, j;
+            pair_ij(ij, i, j);
             double* Wb = Ws + (s & 1) * S::W_SZ;
             constexpr int NB = S::NT * 8;          // padded column count
             constexpr int GPC = (KC * 4) / 3;      // Gauss points per chunk (KC*4 is a multiple of 3)
@@ -247,7 +257,8 @@ implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
                     }
                 }
                 if (ch == S::NCH - 1) {
-                    const int i = ij / NV, j = ij - i * NV;
+                    int i, j;
+                    pair_ij(ij, i, j);
 #pragma unroll
                     for (int m = 0; m < MTW; ++m) {
                         const int a = 8 * (warp + 4 * m) + lr;
@@ -257,7 +268,10 @@ implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
 #pragma unroll
                                 for (int z = 0; z < 2; ++z) {
                                     const int b = 8 * q + 2 * lc + z;
-                                    if (b < NPE) Ke[(size_t)(a * NV + i) * ndof + b * NV + j] = c[m][q][z];
+                                    if (b < NPE) {
+                                        Ke[(size_t)(a * NV + i) * ndof + b * NV + j] = c[m][q][z];
+                                        if (i != j) Ke[(size_t)(b * NV + j) * ndof + a * NV + i] = c[m][q][z];
+                                    }
                                 }
                         }
                     }
