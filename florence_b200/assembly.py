@@ -11,8 +11,6 @@ Objects are duck-typed exactly as the reference reads them.  Host
 (state) or once per mesh (cached handle); results come back as numpy / scipy objects, or stay on the device as torch
 tensors (DLPack-exportable) when `device_out=True`.
 """
-import weakref
-
 import numpy as np
 import torch
 from scipy.sparse import csr_matrix

@@ -15,7 +15,9 @@
  *   (ii) outputs of the reference's own pure-numpy twins of the same formulas
  *        (MaterialLibrary/<Material>.py CauchyStress/Hessian, DisplacementFormulation.
  *        GetLocalStiffness, DisplacementPotentialFormulation.GetLocalStiffness, ...),
- * both committed as fixtures under tests/golden/ together with the generating script.
+ * both committed as fixtures under tests/golden/ together with the generating script, and
+ *   (iii) the reference's own native sparsity-pattern / CSR-scatter code compiled from /root/reference into
+ *        oracle/_ref/libflorence_ref.so (oracle/ref_shim.cpp, tests/test_reference_natives.py).
  *
  * Every function cites the reference file:line (relative to /root/reference) it follows.
  * Third-party arithmetic that is absent from /root/reference: romeric/Fastor (unpinned,

@@ -287,3 +287,66 @@ def explicit_central_difference(T_of, X, M, F_ext_of, dt, nsteps, fixed_mask, ap
         U00, U0 = U0, U                                  # :183-184
         T = T_of(Eulerx)                                 # :188
     return snaps, Eulerx, T
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own natives
+_REF_PATH = os.path.join(_HERE, "_ref", "libflorence_ref.so")
+
+
+def build_ref(reference_root="/root/reference"):
+    """Compile the reference's Fastor-free native headers from where they lie (oracle/Makefile target `ref`).
+    Only possible where the reference checkout exists (the build container); the .so then travels with the repo."""
+    if os.path.isdir(reference_root):
+        subprocess.check_call(["make", "-C", _HERE, "ref", "REF=" + reference_root], stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_PATH)
+
+
+def ref_available():
+    return os.path.exists(_REF_PATH)
+
+
+def ref_sparsity_pattern(elements, nnode, nvar):
+    """ComputeSparsityPattern executed by the REFERENCE's native code (_ComputeSparsityPattern_, _ComputeDataIndices_); the numpy
+    glue around the two calls follows ComputeSparsityPattern.pyx:44-112 line by line."""
+    lib = C.CDLL(_REF_PATH)
+    els = np.asarray(elements)
+    nelem, nodeperelem = els.shape
+    to_c_elements = np.copy(els.astype(np.int32))
+    sorter = np.ascontiguousarray(np.argsort(els, axis=1).astype(np.int64))
+    to_c_elements = np.ascontiguousarray(to_c_elements[np.arange(nelem)[:, None], sorter])
+    flat = np.ascontiguousarray(to_c_elements.ravel())
+    idx_sort = np.argsort(flat, kind="stable").astype(np.int32)
+    sorted_elements = flat[idx_sort]
+    elem_container = np.ascontiguousarray((idx_sort // nodeperelem).astype(np.int32))
+    idx_start = np.zeros(nnode + 1, dtype=np.int32)
+    idx_start[:-1] = np.unique(sorted_elements, return_index=True)[1].astype(np.int32)
+    idx_start[-1] = elem_container.shape[0]
+    counts = np.zeros(idx_start.shape[0] - 1, dtype=np.int32)
+    indices = np.zeros(int((nvar * nodeperelem) ** 2 * nelem), dtype=np.int32)
+    lib.ref_compute_sparsity_pattern.restype = C.c_int
+    nnz = lib.ref_compute_sparsity_pattern(_p(flat), _p(idx_start), _p(elem_container), C.c_int(nvar), C.c_int(nnode), C.c_int(nelem),
+                                           C.c_int(nodeperelem), C.c_int(idx_start.shape[0]), _p(counts), _p(indices))
+    counts = np.repeat(counts, nvar)
+    all_ndof = nnode * nvar
+    indptr = np.zeros(nnode * nvar + 1, dtype=np.int32)
+    indptr[1:] = np.cumsum(np.minimum(counts.astype(np.int64) * nvar, all_ndof)).astype(np.int32)
+    indices = np.ascontiguousarray(indices[:nnz])
+    cap = (nvar * nodeperelem) ** 2
+    dl = np.zeros(cap * nelem, dtype=np.int32)
+    dg = np.zeros(cap * nelem, dtype=np.int32)
+    lib.ref_compute_data_indices(_p(indices), _p(indptr), C.c_int(nelem), C.c_int(nvar), C.c_int(nodeperelem), _p(to_c_elements), _p(sorter),
+                                 _p(dl), _p(dg))
+    return indices, indptr, dl, dg
+
+
+def ref_csr_scatter(Ke_all, dl, dg, nnz):
+    """SparseAssemblyNativeCSR_ (the reference's code) over all elements, in element order: V (nnz)."""
+    lib = C.CDLL(_REF_PATH)
+    Ke_all = _f64(Ke_all)
+    nelem = Ke_all.shape[0]
+    cap = Ke_all.shape[1]
+    V = np.zeros(nnz)
+    for e in range(nelem):
+        row = np.ascontiguousarray(Ke_all[e])
+        lib.ref_sparse_assembly_csr(_p(row), _p(dl), _p(dg), C.c_int(e), C.c_int(cap), _p(V))
+    return V
