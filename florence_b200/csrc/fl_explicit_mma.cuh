@@ -26,14 +26,14 @@ struct mma_shape {
     static constexpr int MT1 = (M1 + 7) / 8, KS1 = (K1 + 3) / 4, NT1 = N1 / 8;
     static constexpr int MT3 = (M3 + 7) / 8, KS3 = (K3 + 3) / 4, NT3 = N3 / 8;
     // leading dimensions == 8 (mod 16): the four 64-byte row segments of a B fragment tile two 128-byte wavefronts exactly
-    static constexpr int LDX = N1 + 8, LDP = N3 % 16 == 8 ? N3 : N3 + 8, LDJ = N1 + 2;
+    static constexpr int LDX = N1 + 8, LDP = N3 % 16 == 8 ? N3 : N3 + 8, LDJ = NPE > 8 ? N1 + 1 : N1 + 2;  // hex27: 3 blocks/SM need the smaller tile; hex8 keeps 16-byte aligned rows
     static constexpr int XX_SZ = KS1 * 4 * LDX, JAC_SZ = MT1 * 8 * LDJ, P_SZ = KS3 * 4 * LDP, TE_SZ = NE * NPE * 3;
     static constexpr int SCR_SZ = JAC_SZ > TE_SZ ? JAC_SZ : TE_SZ;  // te staging aliases the Jacobian tile
     static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * XX_SZ + SCR_SZ + P_SZ);  // coordinates are double-buffered
 };
 
 template <int MAT, int NPE, int NG, int NE, int WM1, int WM3>
-__global__ void __launch_bounds__(MMA_THREADS, 2)
+__global__ void __launch_bounds__(MMA_THREADS, (NPE > 8 ? 3 : 4))
 explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                              const double* __restrict__ jm, const double* __restrict__ gw, int64_t nelem, int ldg, MatParams prm,
                              double* __restrict__ te) {
