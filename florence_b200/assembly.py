@@ -57,19 +57,29 @@ _handle_cache = {}
 
 
 def _array_key(a):
+    """Identity + cheap content fingerprint of a mesh/table array: a mesh that is modified in place (same buffer) must not
+    hit a stale device copy."""
     if isinstance(a, torch.Tensor):
-        return ("t", a.data_ptr(), tuple(a.shape))
+        flat = a.reshape(-1)
+        step = max(1, flat.numel() // 4096)
+        fp = float(flat[::step].double().sum().item()) if flat.numel() else 0.0
+        return ("t", a.data_ptr(), tuple(a.shape), fp)
     a = np.asarray(a)
-    return ("n", a.__array_interface__["data"][0], a.shape)
+    flat = a.reshape(-1)
+    step = max(1, flat.shape[0] // 4096)
+    fp = float(flat[::step].astype(np.float64).sum()) if flat.shape[0] else 0.0
+    return ("n", a.__array_interface__["data"][0], a.shape, fp)
 
 
 def get_handle(mesh, function_space):
-    """Device handle for (mesh, function_space); cached so repeated Newton / time steps do not re-upload the mesh."""
+    """Device handle for (mesh, function_space); cached so repeated Newton / time steps do not re-upload the mesh.
+    A handle owns its scratch buffers: it serves one assembly call at a time (the reference's natives are likewise called with
+    the GIL held)."""
     key = (_array_key(mesh.points), _array_key(mesh.elements), _array_key(function_space.Jm))
     ent = _handle_cache.get(key)
     if ent is not None:
         return ent
-    if len(_handle_cache) >= 8:
+    if len(_handle_cache) >= 4:
         _handle_cache.pop(next(iter(_handle_cache))).close()
     h = AssemblyHandle(mesh.points, mesh.elements, function_space.Jm, function_space.AllGauss, getattr(function_space, "Bases", None))
     _handle_cache[key] = h
@@ -83,20 +93,31 @@ def clear_handles():
 
 
 _pinned = {}
+_PINNED_RING = 2
 
 
 def _to_host(t, tag):
-    """D2H into a cached pinned buffer (returned as a numpy view of it)."""
-    key = (tag, t.dtype, t.numel())
-    buf = _pinned.get(key)
-    if buf is None:
+    """D2H into pinned host memory, returned as a numpy view.  The reference returns freshly allocated arrays; allocating (or
+    page-locking) gigabytes per call would cost more than the assembly itself, so large results rotate through a ring of
+    _PINNED_RING pinned buffers per (tag, size): an array returned by call i stays valid until call i + _PINNED_RING of the same
+    kind -- enough for Newton / time loops, which consume K before re-assembling.  Small results (< 64 MiB) are copied out."""
+    n = t.numel()
+    key = (tag, t.dtype, n)
+    ent = _pinned.get(key)
+    if ent is None:
         if len(_pinned) > 16:
             _pinned.clear()
-        buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
-        _pinned[key] = buf
+        ent = {"bufs": [None] * _PINNED_RING, "next": 0}
+        _pinned[key] = ent
+    k = ent["next"]
+    ent["next"] = (k + 1) % _PINNED_RING
+    if ent["bufs"][k] is None:
+        ent["bufs"][k] = torch.empty(n, dtype=t.dtype, pin_memory=True)
+    buf = ent["bufs"][k]
     buf.copy_(t.reshape(-1), non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return buf.numpy()
+    out = buf.numpy()
+    return out.copy() if out.nbytes < (64 << 20) else out
 
 
 def _state_to_device(h, Eulerx, Eulerp):
@@ -117,11 +138,11 @@ def _implicit(matname, fields, fem_solver, function_space, formulation, mesh, ma
         I, J, V, T = h.assemble_implicit(x, p, mat, form, update, mode="coo")
         if device_out:
             return I, J, V, T
-        return _to_host(I, "I"), _to_host(J, "J"), _to_host(V, "V"), _to_host(T, "T").copy()
+        return _to_host(I, "I"), _to_host(J, "J"), _to_host(V, "V"), _to_host(T, "T")
     V, T = h.assemble_implicit(x, p, mat, form, update, mode="csr")
     if device_out:
         return V, T
-    return _to_host(V, "V"), _to_host(T, "T").copy()
+    return _to_host(V, "V"), _to_host(T, "T")
 
 
 def _stamp(matname, fields):
@@ -184,7 +205,7 @@ def _LowLevelAssemblyExplicit_DF_DPF_(function_space, formulation, mesh, materia
         raise NotImplementedError("Explicit low level assembly for {} is not available".format(formulation.fields))
     x, p = _state_to_device(h, Eulerx, Eulerp)
     T = h.assemble_explicit(x, p, mat, form)
-    return T if device_out else _to_host(T, "Te").copy()
+    return T if device_out else _to_host(T, "Te")
 
 
 def _LowLevelAssemblyExplicit_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
