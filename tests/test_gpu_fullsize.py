@@ -106,3 +106,63 @@ def test_config3_hex27_neohookean_explicit_8M_elements():
     To = orc.assemble_explicit(P, remap[E], X, None, Jm, AG, 3, orc.params(mu=mu, lamb=lamb), 1)
     assert np.linalg.norm(Tl - To) <= 1e-11 * np.linalg.norm(To)
     hs.close(); h.close()
+
+
+def test_config1_poisson_p4_hex_6cubed():
+    """BASELINE.json configs[0]: simple_laplace -- Poisson on a 6^3 hex mesh, p=4 (hex125), IdealDielectric eps=2.35; the whole
+    K against the oracle (the CPU-runnable case of the reference)."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    from scipy.sparse import csr_matrix
+    pts, els = flmesh.box_hex_mesh(6, 6, 6, p=4)
+    assert els.shape == (216, 125) and pts.shape == (15625, 3)
+    Bases, Jm, AG = flmesh.tables("hex", 4)
+    e = -2.35 * np.eye(3)                                  # the wrapper passes -material.e (.pyx:81)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases)
+    indices, indptr = h.sparsity_pattern(1)
+    V = h.assemble_laplacian(e, True, mode="csr").cpu().numpy()
+    pat = orc.sparsity_pattern(els.numpy(), pts.shape[0], 1)
+    assert np.array_equal(indices.cpu().numpy(), pat[0]) and np.array_equal(indptr.cpu().numpy(), pat[1])
+    Vo = orc.assemble_laplacian(pts.numpy(), els.numpy(), Jm, AG, e, True, mode="csr", pattern=pat)
+    assert np.abs(V - Vo).max() <= 1e-10 * np.abs(Vo).max()
+    K = csr_matrix((V, pat[0], pat[1]), shape=(15625, 15625))
+    assert abs(K - K.T).max() == 0.0                       # upper triangle mirrored, as the reference does for a symmetric tensor
+    assert np.abs(K @ np.ones(15625)).max() <= 1e-10 * np.abs(V).max()   # constants are in the null space
+    h.close()
+
+
+def test_config5_hex8_mooney_rivlin_explicit_8M_elements():
+    from florence_b200 import backend, mesh as flmesh
+    dev = torch.device("cuda:0")
+    n = 200
+    pts, els = flmesh.box_hex_mesh(n, n, n, p=1, device=dev)
+    assert els.shape == (8000000, 8)
+    Bases, Jm, AG = flmesh.tables("hex", 1)
+    x = flmesh.perturbed_state(pts, 1.0 / n, 0.02, seed=0)
+    mu1, nu = 1.0e6, 0.495
+    lamb = 2.0 * mu1 * nu / (1.0 - 2.0 * nu)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases, device=dev)
+    mat = backend.make_material(2, 8000.0, mu1=mu1, mu2=0.0, lamb=lamb)
+    T = h.assemble_explicit(x, None, mat, 0)
+    Tmax = float(T.abs().max())
+    assert torch.equal(T, h.assemble_explicit(x, None, mat, 0))
+    assert float(T.view(-1, 3).sum(0).abs().max()) <= 1e-8 * Tmax * 1e3
+    h.set_option(0, 0)
+    Ts = h.assemble_explicit(x, None, mat, 0)
+    h.set_option(0, 1)
+    assert float((Ts - T).abs().max()) <= 1e-11 * Tmax
+    # ExplicitMooneyRivlin (stress-only kernel of the car-crash example) gives the same forces
+    mat0 = backend.make_material(0, 8000.0, mu1=mu1, mu2=0.0, lamb=lamb)
+    assert torch.equal(h.assemble_explicit(x, None, mat0, 0), T)
+    # ten device-resident central-difference steps stay finite and move only free dofs
+    M = h.assemble_mass(8000.0, 3, "lumped")
+    assert abs(float(M.sum()) / 3.0 - 8000.0) <= 1e-9 * 8000.0          # total mass of the unit cube
+    fixed = torch.zeros(pts.shape[0] * 3, dtype=torch.uint8, device=dev)
+    fixed[: 3 * (n + 1) * (n + 1)] = 1                                   # clamp the z = 0 plane
+    Eulerx = x.reshape(-1).clone()
+    U0 = torch.zeros_like(T); U00 = torch.zeros_like(T)
+    dt = 0.2 * (1.0 / n) / np.sqrt((lamb + 2 * mu1) / 8000.0)
+    status = h.explicit_steps(mat, dt, 10, 2, M, None, fixed, None, U0, U00, Eulerx, T)
+    assert status == 0 and bool(torch.isfinite(Eulerx).all())
+    assert float((Eulerx - pts.reshape(-1))[: 3 * (n + 1) * (n + 1)].abs().max()) == 0.0
+    h.close()

@@ -72,6 +72,12 @@ def test_low_level_assembly_dispatch(key, fields):
     check(K2, T2)
     V, T3 = assembly._LowLevelAssembly_Par_(so, fs, fo, me, mat, Eulerx, Eulerp)
     assert V.shape == so.indices.shape
+    # squeeze_sparsity_pattern=True: only (indices, indptr) are returned and the same V comes back (binary-search mode of the reference)
+    sq = assembly.ComputeSparsityPattern(me, nvar, squeeze_sparsity_pattern=True, function_space=fs)
+    assert len(sq) == 2 and np.array_equal(sq[0], so.indices)
+    so.squeeze_sparsity_pattern = True
+    V2, _ = assembly._LowLevelAssembly_Par_(so, fs, fo, me, mat, Eulerx, Eulerp)
+    assert np.array_equal(V2, V)
     # explicit entry points
     if so.requires_geometry_update:
         Te, F, M = assembly._LowLevelAssemblyExplicit_(so, fs, fo, me, mat, Eulerx, Eulerp)
