@@ -15,7 +15,8 @@ FL_MODE_COO, FL_MODE_CSR = 0, 1
 # every symbol include/florence_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ["fl_last_error", "fl_version", "fl_create", "fl_destroy", "fl_assemble_explicit", "fl_pattern_build", "fl_pattern_export",
            "fl_pattern_export_data_indices", "fl_assemble_implicit", "fl_assemble_laplacian", "fl_assemble_mass", "fl_explicit_steps",
-           "fl_pack_nodes", "fl_unpack_add_nodes", "fl_explicit_update", "fl_measure_fp64_peak", "fl_set_timing", "fl_get_timing", "fl_set_option"]
+           "fl_pack_nodes", "fl_unpack_add_nodes", "fl_explicit_update", "fl_measure_fp64_peak", "fl_set_timing", "fl_get_timing", "fl_set_option",
+           "fl_dirichlet_build", "fl_dirichlet_export", "fl_dirichlet_apply", "fl_set_contact", "fl_assemble_contact"]
 
 
 class MeshDesc(C.Structure):
@@ -59,6 +60,11 @@ def load():
     lib.fl_pattern_build.argtypes = [vp, i32, C.POINTER(i64)]
     lib.fl_pattern_export.argtypes = [vp, i32, vp, vp, vp]
     lib.fl_pattern_export_data_indices.argtypes = [vp, i32, vp, vp, vp]
+    lib.fl_dirichlet_build.argtypes = [vp, i32, vp, i64, C.POINTER(i64), C.POINTER(i64)]
+    lib.fl_dirichlet_export.argtypes = [vp, vp, vp, vp, vp]
+    lib.fl_dirichlet_apply.argtypes = [vp, vp, vp, vp, dbl, vp, vp, vp]
+    lib.fl_set_contact.argtypes = [vp, vp, i64, vp, dbl, dbl, dbl, vp]
+    lib.fl_assemble_contact.argtypes = [vp, vp, vp, i32, vp]
     lib.fl_assemble_implicit.argtypes = [vp, vp, vp, C.POINTER(Material), i32, i32, i32, vp, vp, vp, vp, vp]
     lib.fl_assemble_laplacian.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     lib.fl_assemble_mass.argtypes = [vp, dbl, i32, i32, i32, vp, vp, vp, vp, vp]

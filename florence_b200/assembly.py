@@ -96,7 +96,7 @@ _pinned = {}
 _PINNED_RING = 2
 
 
-def _to_host(t, tag):
+def _to_host(t, tag, defer=False):
     """D2H into pinned host memory, returned as a numpy view.  The reference returns freshly allocated arrays; allocating (or
     page-locking) gigabytes per call would cost more than the assembly itself, so large results rotate through a ring of
     _PINNED_RING pinned buffers per (tag, size): an array returned by call i stays valid until call i + _PINNED_RING of the same
@@ -115,9 +115,30 @@ def _to_host(t, tag):
         ent["bufs"][k] = torch.empty(n, dtype=t.dtype, pin_memory=True)
     buf = ent["bufs"][k]
     buf.copy_(t.reshape(-1), non_blocking=True)
+    if defer:
+        ev = torch.cuda.Event()
+        ev.record()
+        return buf, ev
     torch.cuda.current_stream().synchronize()
+    return _finish_host(buf)
+
+
+def _finish_host(buf):
     out = buf.numpy()
     return out.copy() if out.nbytes < (64 << 20) else out
+
+
+def _to_host_many(items):
+    """D2H of several results with the copies queued back to back, small ones first: the host-side copy-out of a small result
+    (T) runs while the large one (the K values) is still crossing PCIe."""
+    order = sorted(range(len(items)), key=lambda i: items[i][0].numel())
+    pend = {i: _to_host(items[i][0], items[i][1], defer=True) for i in order}
+    out = [None] * len(items)
+    for i in order:
+        buf, ev = pend[i]
+        ev.synchronize()
+        out[i] = _finish_host(buf)
+    return tuple(out)
 
 
 def _state_to_device(h, Eulerx, Eulerp):
@@ -138,11 +159,11 @@ def _implicit(matname, fields, fem_solver, function_space, formulation, mesh, ma
         I, J, V, T = h.assemble_implicit(x, p, mat, form, update, mode="coo")
         if device_out:
             return I, J, V, T
-        return _to_host(I, "I"), _to_host(J, "J"), _to_host(V, "V"), _to_host(T, "T")
+        return _to_host_many([(I, "I"), (J, "J"), (V, "V"), (T, "T")])
     V, T = h.assemble_implicit(x, p, mat, form, update, mode="csr")
     if device_out:
         return V, T
-    return _to_host(V, "V"), _to_host(T, "T")
+    return _to_host_many([(V, "V"), (T, "T")])
 
 
 def _stamp(matname, fields):

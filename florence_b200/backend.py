@@ -140,6 +140,71 @@ class AssemblyHandle(object):
             check(self.lib.fl_pattern_export_data_indices(self._h, nvar, _ptr(dl), _ptr(dg), _stream()))
         return indices, indptr, dl, dg
 
+    # ---------------------------------------------------------------------------------------------- penalty contact
+    def set_contact(self, surface_nodes, plane_normal, distance, kappa, contact_gap_tolerance=1e-6):
+        """Members of ExplicitPenaltyContactFormulation (:14-24) + the unique nodes of mesh.faces / mesh.edges (:157-160).
+        surface_nodes=None switches contact off."""
+        with torch.cuda.device(self.device):
+            if surface_nodes is None:
+                check(self.lib.fl_set_contact(self._h, None, 0, None, 0.0, 0.0, 0.0, _stream()))
+                return
+            ids = to_device(surface_nodes, torch.int32, self.device).reshape(-1)
+            nrm = (C.c_double * 3)(*[float(v) for v in np.asarray(plane_normal, dtype=np.float64).ravel()[:self.ndim]])
+            check(self.lib.fl_set_contact(self._h, _ptr(ids), ids.numel(), C.cast(nrm, C.c_void_p), float(distance), float(kappa),
+                                          float(contact_gap_tolerance), _stream()))
+
+    def assemble_contact(self, Eulerx, out=None, accumulate=False):
+        """AssembleTractions (:145-184): T_contact (nnode*ndim), or `out += T_contact` when accumulate."""
+        x = to_device(Eulerx, torch.float64, self.device)
+        T = out if out is not None else torch.empty(self.nnode * self.ndim, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_assemble_contact(self._h, _ptr(x), _ptr(T), 1 if accumulate else 0, _stream()))
+        return T
+
+    # ---------------------------------------------------------------------------------------------- Dirichlet reduction
+    def dirichlet_build(self, nvar, columns_out):
+        """Prescribed dofs (ascending) -> (n_in, nnz_b); BoundaryCondition.py:375-396 builds the same two lists on the host."""
+        self.build_pattern(nvar)
+        co = to_device(columns_out, torch.int32, self.device).reshape(-1)
+        n_in, nnz_b = C.c_int64(0), C.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_dirichlet_build(self._h, nvar, _ptr(co) if co.numel() else None, co.numel(), C.byref(n_in), C.byref(nnz_b)))
+        self._dirichlet = (nvar, int(n_in.value), int(nnz_b.value), co.numel())
+        return int(n_in.value), int(nnz_b.value)
+
+    def dirichlet_pattern(self):
+        """(indices_b, indptr_b, columns_in) int32 device tensors of K[columns_in,:][:,columns_in]."""
+        nvar, n_in, nnz_b, _ = self._dirichlet
+        indptr = torch.empty(n_in + 1, dtype=torch.int32, device=self.device)
+        indices = torch.empty(nnz_b, dtype=torch.int32, device=self.device)
+        cin = torch.empty(n_in, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_dirichlet_export(self._h, _ptr(indptr), _ptr(indices), _ptr(cin), _stream()))
+        return indices, indptr, cin
+
+    def dirichlet_apply(self, V=None, F=None, applied=None, load_factor=1.0, want_values=True, want_reduced_force=True, out=None):
+        """One pass over the free rows: V_b = values of V[in][:, in]; F[in] -= V[in][:, out(nz)] @ applied(nz) * load_factor (in
+        place); F_b = F[in].  Returns (V_b or None, F_b or None)."""
+        nvar, n_in, nnz_b, n_out = self._dirichlet
+        Vb = Fb = None
+        if out is not None:
+            Vb, Fb = out
+        if want_values and Vb is None:
+            Vb = torch.empty(nnz_b, dtype=torch.float64, device=self.device)
+        if want_reduced_force and Fb is None:
+            Fb = torch.empty(n_in, dtype=torch.float64, device=self.device)
+        if applied is not None:
+            applied = to_device(applied, torch.float64, self.device).reshape(-1)
+            if applied.numel() != n_out:
+                raise ValueError("AppliedDirichlet has %d entries, columns_out has %d" % (applied.numel(), n_out))
+        if F is not None and (F.dtype != torch.float64 or not F.is_contiguous() or F.numel() != self.nnode * nvar):
+            raise ValueError("F must be a contiguous float64 device tensor of nvar*nnode entries")
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_dirichlet_apply(self._h, _ptr(V) if V is not None else None, _ptr(Vb) if want_values else None,
+                                              _ptr(applied) if applied is not None else None, float(load_factor),
+                                              _ptr(F) if F is not None else None, _ptr(Fb) if want_reduced_force else None, _stream()))
+        return (Vb if want_values else None), (Fb if want_reduced_force else None)
+
     # ---------------------------------------------------------------------------------------------- implicit
     def assemble_implicit(self, Eulerx, Eulerp, material, formulation_number=0, requires_geometry_update=True, mode="csr",
                           out=None, with_indices=True):

@@ -186,6 +186,8 @@ int fl_destroy(fl_handle* h) {
     for (int k = 0; k < 4; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->jmT); cudaFree(h->bases); cudaFree(h->gw);
     cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank);
+    dirichlet_free(h);
+    cudaFree(h->contact.surf);
     cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag);
     delete h;
     return FL_OK;
@@ -224,6 +226,69 @@ int fl_pattern_export(fl_handle* h, int nvar, int32_t* indptr, int32_t* indices,
 int fl_pattern_export_data_indices(fl_handle* h, int nvar, int32_t* dl, int32_t* dg, void* stream) {
     if (!h || !dl || !dg) { set_error("null argument"); return FL_ERR_INVALID; }
     return launch_data_indices(h, nvar, dl, dg, (cudaStream_t)stream);
+}
+
+__global__ void flag_nodes_kernel(const int32_t* __restrict__ ids, int64_t n, int64_t nnode, uint8_t* __restrict__ flags, int32_t* bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = ids[i];
+    if (k < 0 || k >= nnode) { *bad = 1; return; }
+    flags[k] = 1;
+}
+
+int fl_set_contact(fl_handle* h, const int32_t* surface_nodes, int64_t n_surface, const double* plane_normal, double distance, double kappa,
+                   double contact_gap_tolerance, void* stream) {
+    if (!h) { set_error("null argument"); return FL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_surface <= 0) {
+        FL_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(h->contact.surf);
+        h->contact = Contact();
+        return FL_OK;
+    }
+    if (!surface_nodes || !plane_normal) { set_error("null argument"); return FL_ERR_INVALID; }
+    uint8_t* flags = nullptr;
+    FL_CUDA_CHECK(cudaMalloc(&flags, h->nnode > 0 ? h->nnode : 1));
+    FL_CUDA_CHECK(cudaMemsetAsync(flags, 0, h->nnode, st));
+    FL_CUDA_CHECK(cudaMemsetAsync(h->flag, 0, sizeof(int32_t), st));
+    flag_nodes_kernel<<<(unsigned)((n_surface + 255) / 256), 256, 0, st>>>(surface_nodes, n_surface, h->nnode, flags, h->flag);
+    int32_t bad = 0;
+    FL_CUDA_CHECK(cudaMemcpyAsync(&bad, h->flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FL_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (bad) { cudaFree(flags); set_error("surface node id out of range"); return FL_ERR_INVALID; }
+    cudaFree(h->contact.surf);
+    h->contact = Contact();
+    h->contact.surf = flags;
+    for (int i = 0; i < h->ndim; ++i) h->contact.n[i] = plane_normal[i];
+    h->contact.L = distance;
+    h->contact.kappa = kappa;
+    h->contact.tol = contact_gap_tolerance;
+    return FL_OK;
+}
+
+int fl_assemble_contact(fl_handle* h, const double* Eulerx, double* T, int accumulate, void* stream) {
+    if (!h || !Eulerx || !T) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_contact(h, Eulerx, T, accumulate ? 1 : 0, (cudaStream_t)stream);
+}
+
+int fl_dirichlet_build(fl_handle* h, int nvar, const int32_t* columns_out, int64_t n_out, int64_t* n_in_host, int64_t* nnz_b_host) {
+    if (!h || nvar < 1 || nvar > 4 || (n_out > 0 && !columns_out)) { set_error("bad argument"); return FL_ERR_INVALID; }
+    int rc = dirichlet_build(h, nvar, columns_out, n_out);
+    if (rc) return rc;
+    if (n_in_host) *n_in_host = h->dir.n_in;
+    if (nnz_b_host) *nnz_b_host = h->dir.nnz_b;
+    return FL_OK;
+}
+
+int fl_dirichlet_export(fl_handle* h, int32_t* indptr_b, int32_t* indices_b, int32_t* columns_in, void* stream) {
+    if (!h) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_dirichlet_export(h, indptr_b, indices_b, columns_in, (cudaStream_t)stream);
+}
+
+int fl_dirichlet_apply(fl_handle* h, const double* V, double* V_b, const double* applied, double load_factor, double* F, double* F_b,
+                       void* stream) {
+    if (!h) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_dirichlet_apply(h, V, V_b, applied, load_factor, F, F_b, (cudaStream_t)stream);
 }
 
 static int scatter_stiffness(fl_handle* h, int nvar, int mode, double* ke, int32_t* I, int32_t* J, double* V, cudaStream_t st) {
@@ -336,6 +401,10 @@ int fl_explicit_steps(fl_handle* h, const fl_material* mat, const fl_explicit_ct
     if (c->nsteps > 0) {
         rc = launch_gather_nodes(h, nvar, h->te, T, st);
         if (rc) return rc;
+        if (h->contact.surf) {   // the returned T is the reference's TractionForces: internal + contact at the final geometry
+            rc = launch_contact(h, Eulerx, T, 1, st);
+            if (rc) return rc;
+        }
     }
     if (status_host) {
         FL_CUDA_CHECK(cudaMemcpyAsync(status_host, h->flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

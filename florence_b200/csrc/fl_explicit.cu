@@ -196,7 +196,7 @@ __global__ void explicit_update_kernel(const int64_t* __restrict__ adj_ptr, cons
                                        const double* __restrict__ fext, const uint8_t* __restrict__ fixed,
                                        const double* __restrict__ inc_dir, const double* __restrict__ X, double* __restrict__ T,
                                        int write_T, double* __restrict__ U0, double* __restrict__ U00, double* __restrict__ Eulerx,
-                                       int32_t* __restrict__ nan_flag) {
+                                       int32_t* __restrict__ nan_flag, const Contact contact) {
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= nnode) return;
     double t[D];
@@ -208,6 +208,17 @@ __global__ void explicit_update_kernel(const int64_t* __restrict__ adj_ptr, cons
             const int64_t idx = adj_idx[k];
 #pragma unroll
             for (int i = 0; i < D; ++i) t[i] += te[idx * D + i];
+        }
+        // TractionForces += contact tractions evaluated at the geometry the element forces were computed on
+        // (ExplicitStructuralDynamicIntegrator.py:190-197); a caller-supplied T (FUSED = false) already contains them
+        if (contact.surf && contact.surf[n]) {
+            double xo[D], fc[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) xo[i] = Eulerx[n * D + i];
+            if (contact_force<D>(contact, xo, fc)) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) t[i] = __dadd_rn(t[i], fc[i]);
+            }
         }
         if (write_T) {
 #pragma unroll
@@ -348,13 +359,45 @@ int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, dou
     const int write_T = (fused_gather == 2);
 #define FL_UPD(D_, F_)                                                                                                     \
     explicit_update_kernel<D_, F_><<<blocks, threads, 0, st>>>(h->adj_ptr, h->adj_idx, te, h->nnode, dt, fext_scale, M, fext, fixed, \
-                                                               inc_dir, h->points, T, write_T, U0, U00, Eulerx, nan_flag)
+                                                               inc_dir, h->points, T, write_T, U0, U00, Eulerx, nan_flag, h->contact)
     if (h->ndim == 3) {
         if (fused_gather) FL_UPD(3, true); else FL_UPD(3, false);
     } else {
         if (fused_gather) FL_UPD(2, true); else FL_UPD(2, false);
     }
 #undef FL_UPD
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+// AssembleTractions of the contact formulation as a stand-alone pass: T (+)= kappa * gap * n on the contact nodes
+template <int D>
+__global__ void contact_kernel(const Contact c, const double* __restrict__ x, int64_t nnode, double* __restrict__ T, int accumulate) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nnode) return;
+    double xo[D], fc[D];
+    bool hit = false;
+    if (c.surf[n]) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) xo[i] = x[n * D + i];
+        hit = contact_force<D>(c, xo, fc);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if (accumulate) {
+            if (hit) T[n * D + i] = __dadd_rn(T[n * D + i], fc[i]);
+        } else {
+            T[n * D + i] = hit ? fc[i] : 0.0;
+        }
+    }
+}
+
+int launch_contact(fl_handle* h, const double* Eulerx, double* T, int accumulate, cudaStream_t st) {
+    if (!h->contact.surf) { set_error("fl_set_contact has not been called"); return FL_ERR_STATE; }
+    if (h->nnode == 0) return FL_OK;
+    const unsigned blocks = (unsigned)((h->nnode + 255) / 256);
+    if (h->ndim == 3) contact_kernel<3><<<blocks, 256, 0, st>>>(h->contact, Eulerx, h->nnode, T, accumulate);
+    else contact_kernel<2><<<blocks, 256, 0, st>>>(h->contact, Eulerx, h->nnode, T, accumulate);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }

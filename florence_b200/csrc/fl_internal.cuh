@@ -32,6 +32,35 @@ struct Pattern {
     int max_cnt = 0;           // widest row in nodes
 };
 
+// Dirichlet reduction (fl_dirichlet.cu): free/prescribed dof maps and the row pointer of K[columns_in][:, columns_in]
+struct Dirichlet {
+    int nvar = 0;
+    int64_t n_in = 0, n_out = 0, nnz_b = 0;
+    int32_t* new_id = nullptr;    // nvar*nnode: reduced index of a free dof, -(k+1) for the k-th prescribed dof
+    int32_t* cols_in = nullptr;   // n_in
+    int64_t* rowptr_b = nullptr;  // n_in+1
+};
+
+// Rigid-plane penalty contact (ExplicitPenaltyContactFormulation.py:145-184): nodes flagged in `surf` (the unique nodes of the
+// boundary faces) with gap = x.n + L < tol receive the force kappa*gap*n.
+struct Contact {
+    uint8_t* surf = nullptr;   // nnode flags; nullptr = no contact
+    double n[3] = {0, 0, 0};
+    double L = 0, kappa = 0, tol = 0;
+};
+
+template <int D>
+__device__ __forceinline__ bool contact_force(const Contact& c, const double* __restrict__ x, double* f) {
+    double gap = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) gap = __dadd_rn(gap, __dmul_rn(x[i], c.n[i]));
+    gap = __dadd_rn(gap, c.L);
+    if (!(gap < c.tol)) return false;
+#pragma unroll
+    for (int i = 0; i < D; ++i) f[i] = __dmul_rn(c.kappa, __dmul_rn(gap, c.n[i]));
+    return true;
+}
+
 }  // namespace fl
 
 struct fl_handle {
@@ -50,6 +79,8 @@ struct fl_handle {
     int32_t* adj_idx = nullptr;  // nelem*npe
     int max_adj = 0;
     fl::Pattern pat;
+    fl::Dirichlet dir;
+    fl::Contact contact;
     // scratch (grown on demand)
     double* te = nullptr;  size_t te_bytes = 0;   // per-element traction buffer nelem*ndof
     double* ke = nullptr;  size_t ke_bytes = 0;   // per-element stiffness buffer nelem*ndof^2 (CSR mode)
@@ -73,6 +104,7 @@ int launch_gather_nodes(fl_handle* h, int nvar, const double* te, double* T, cud
 int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, double dt, double fext_scale, const double* M,
                            const double* fext, const uint8_t* fixed, const double* inc_dir, double* T, double* U0, double* U00,
                            double* Eulerx, int32_t* nan_flag, cudaStream_t st);
+int launch_contact(fl_handle* h, const double* Eulerx, double* T, int accumulate, cudaStream_t st);
 // fl_implicit.cu
 int launch_implicit_elements(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation,
                              int update, double* ke, double* te, cudaStream_t st);
@@ -85,5 +117,11 @@ int launch_pattern_export(fl_handle* h, int nvar, int32_t* indptr, int32_t* indi
 int launch_data_indices(fl_handle* h, int nvar, int32_t* dl, int32_t* dg, cudaStream_t st);
 int launch_coo_indices(fl_handle* h, int nvar, int32_t* I, int32_t* J, cudaStream_t st);
 int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st);
+// fl_dirichlet.cu
+void dirichlet_free(fl_handle* h);
+int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_out);
+int launch_dirichlet_export(fl_handle* h, int32_t* indptr_b, int32_t* indices_b, int32_t* columns_in, cudaStream_t st);
+int launch_dirichlet_apply(fl_handle* h, const double* V, double* V_b, const double* applied, double load_factor, double* F, double* F_b,
+                           cudaStream_t st);
 
 }  // namespace fl

@@ -268,6 +268,17 @@ def make_mesh(element_type, n, p, lengths=None, device="cpu"):
     raise ValueError(element_type)
 
 
+def boundary_nodes(points, tol=1e-12):
+    """Sorted ids of the nodes on the surface of an axis-aligned box mesh -- np.unique(mesh.faces) (np.unique(mesh.edges) in 2-D) of
+    the reference's Mesh for these structured boxes (ExplicitPenaltyContactFormulation.py:157-161 consumes exactly that list)."""
+    is_t = isinstance(points, torch.Tensor)
+    P = points if is_t else torch.as_tensor(np.asarray(points))
+    lo, hi = P.min(0).values, P.max(0).values
+    on = ((P - lo).abs() <= tol * (1 + hi.abs())) | ((P - hi).abs() <= tol * (1 + hi.abs()))
+    ids = torch.nonzero(on.any(1)).reshape(-1)
+    return ids if is_t else ids.numpy()
+
+
 def perturbed_state(points, h, amplitude=0.02, seed=0):
     """Eulerx = X + amplitude*h*U(-1,1) per node, generated on the tensor's device with a fixed seed."""
     gen = torch.Generator(device=points.device)

@@ -6,7 +6,10 @@ Replaces the time loop of ExplicitStructuralDynamicIntegrator.Solver
 [fused node-reduction + update kernel] -> [element internal-force kernel]; the host only sees the snapshots it asks for
 (`save_frequency`) and the blow-up flag.  With an InterfaceExchange the loop becomes force -> exchange -> update per step.
 
-Out of scope, as in SURVEY.md H6: electro-mechanics (needs an implicit Poisson solve every step), consistent mass, contact.
+Rigid-plane penalty contact (ExplicitPenaltyContactFormulation.AssembleTractions, called at :190-197) runs inside the same
+kernels: pass `contact=` (an object with plane_normal, distance, kappa, contact_gap_tolerance) and the surface node list.
+
+Out of scope, as in SURVEY.md H6: electro-mechanics (needs an implicit Poisson solve every step), consistent mass.
 """
 import numpy as np
 import torch
@@ -16,10 +19,17 @@ from . import backend
 
 class ExplicitStructuralDynamicIntegrator(object):
 
-    def __init__(self, handle, material, M=None, rho=None, exchange=None):
+    def __init__(self, handle, material, M=None, rho=None, exchange=None, contact=None, surface_nodes=None):
         self.h = handle
         self.mat = material
         self.exchange = exchange
+        self.has_contact = contact is not None
+        if self.has_contact:
+            # fem_solver.contact_formulation of the reference (FEMSolver.py:215-218); surface_nodes = np.unique(mesh.faces)
+            handle.set_contact(surface_nodes, contact.plane_normal, contact.distance, contact.kappa,
+                               getattr(contact, "contact_gap_tolerance", 1e-6))
+        else:
+            handle.set_contact(None, None, 0.0, 0.0)
         self.nnode, self.ndim = handle.nnode, handle.ndim
         dev = handle.device
         if M is None:
@@ -32,9 +42,12 @@ class ExplicitStructuralDynamicIntegrator(object):
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def internal_force(self, Eulerx, out=None):
+        """TractionForces of the loop: AssembleExplicit (+ interface sum) (+ contact tractions, :190-197)."""
         T = self.h.assemble_explicit(Eulerx, None, self.mat, 0, out=out)
         if self.exchange is not None:
             self.exchange(T)
+        if self.has_contact:
+            self.h.assemble_contact(Eulerx, out=T, accumulate=True)
         return T
 
     def initialise(self, X, fext0, fixed_mask, dt):
@@ -44,7 +57,10 @@ class ExplicitStructuralDynamicIntegrator(object):
         self.X = backend.to_device(X, torch.float64, dev).reshape(-1)
         self.fixed = backend.to_device(fixed_mask, torch.uint8, dev).reshape(-1)
         self.Eulerx = self.X.clone()
-        self.T = self.internal_force(self.Eulerx.view(self.nnode, self.ndim))
+        # the reference's first TractionForces comes from FEMSolver's initial Assemble, before any contact check
+        self.T = self.h.assemble_explicit(self.Eulerx.view(self.nnode, self.ndim), None, self.mat, 0)
+        if self.exchange is not None:
+            self.exchange(self.T)
         f0 = torch.zeros_like(self.T) if fext0 is None else backend.to_device(fext0, torch.float64, dev).reshape(-1)
         A0 = (f0 - self.T) / self.M
         self.U0 = torch.zeros_like(self.T)
@@ -111,7 +127,11 @@ class ExplicitStructuralDynamicIntegrator(object):
         ndim, nnode = formulation.ndim, mesh.points.shape[0]
         LoadIncrement = fem_solver.number_of_load_increments
         dt = fem_solver.total_time / LoadIncrement
-        self = cls(h, mat, M=np.asarray(M, dtype=np.float64).ravel())
+        contact = getattr(fem_solver, "contact_formulation", None) if getattr(fem_solver, "has_contact", False) else None
+        surface = None
+        if contact is not None:
+            surface = np.unique(mesh.edges if ndim == 2 else mesh.faces).astype(np.int64)      # ExplicitPenaltyContactFormulation.py:157-161
+        self = cls(h, mat, M=np.asarray(M, dtype=np.float64).ravel(), contact=contact, surface_nodes=surface)
         NeumannForces = np.asarray(NeumannForces, dtype=np.float64)
         if NeumannForces.ndim == 1:
             NeumannForces = NeumannForces[:, None]

@@ -89,6 +89,35 @@ int fl_pattern_export(fl_handle *h, int nvar, int32_t *indptr, int32_t *indices,
  * the device path uses its own compact node-rank map instead). */
 int fl_pattern_export_data_indices(fl_handle *h, int nvar, int32_t *data_local_indices, int32_t *data_global_indices, void *stream);
 
+/* Rigid-plane penalty contact of the explicit solver: ExplicitPenaltyContactFormulation.AssembleTractions
+ * (Florence/VariationalPrinciple/ExplicitPenaltyContactFormulation.py:145-184), added to the internal forces after every
+ * AssembleExplicit (Florence/TimeIntegrators/ExplicitStructuralDynamicIntegrator.py:190-197).
+ * fl_set_contact: surface_nodes (device int32, the unique nodes of mesh.faces / mesh.edges), plane_normal (HOST, ndim doubles),
+ *   distance, kappa, contact_gap_tolerance as the formulation's members; n_surface = 0 switches contact off.
+ *   While set, fl_explicit_steps adds the contact tractions to every internal force it evaluates (and to the T it returns).
+ * fl_assemble_contact: accumulate = 0 -> T = T_contact (zeros elsewhere, what AssembleTractions returns);
+ *                      accumulate = 1 -> T += T_contact. */
+int fl_set_contact(fl_handle *h, const int32_t *surface_nodes, int64_t n_surface, const double *plane_normal, double distance,
+                   double kappa, double contact_gap_tolerance, void *stream);
+int fl_assemble_contact(fl_handle *h, const double *Eulerx, double *T, int accumulate, void *stream);
+
+/* Dirichlet reduction on the device: BoundaryCondition.GetReducedMatrices and
+ * BoundaryCondition.ApplyDirichletGetReducedMatrices (Florence/BoundaryCondition/BoundaryCondition.py:842-858, :861-891),
+ * which the reference runs with scipy fancy indexing on the host in every Newton iteration (Florence/Solver/FEMSolver.py:951).
+ * fl_dirichlet_build: columns_out (device, int32, strictly ascending) are the prescribed dofs (BoundaryCondition.py:375-396);
+ *   builds the free/prescribed maps and the pattern of K[columns_in,:][:,columns_in]; returns n_in and its nnz.
+ *   Requires fl_pattern_build(nvar).
+ * fl_dirichlet_export: int32 indptr_b (n_in+1), indices_b (nnz_b), columns_in (n_in); any pointer may be NULL.
+ * fl_dirichlet_apply: V = CSR values aligned with fl_pattern_export (stiffness or consistent mass).
+ *   V_b (nnz_b, may be NULL)        <- values of V[columns_in,:][:,columns_in]                         (:850, :884)
+ *   applied (n_out, may be NULL)    -> F[columns_in] -= (V[columns_in,:][:,columns_out[nz]] @ applied[nz]) * load_factor,
+ *                                      nz = ~isclose(applied, 0), summed like scipy's csr_matvec          (:873-875)
+ *   F (nvar*nnode, in place; may be NULL when neither applied nor F_b is given), F_b (n_in, may be NULL) <- F[columns_in]. */
+int fl_dirichlet_build(fl_handle *h, int nvar, const int32_t *columns_out, int64_t n_out, int64_t *n_in_host, int64_t *nnz_b_host);
+int fl_dirichlet_export(fl_handle *h, int32_t *indptr_b, int32_t *indices_b, int32_t *columns_in, void *stream);
+int fl_dirichlet_apply(fl_handle *h, const double *V, double *V_b, const double *applied, double load_factor, double *F,
+                       double *F_b, void *stream);
+
 /* Implicit K and T: _GlobalAssemblyDF_<Material> / _GlobalAssemblyDPF_<Material>
  * (Florence/FiniteElements/Assembly/_Assembly_/_LowLevelAssemblyDF_.h:8-176, _LowLevelAssemblyDPF_.h:45-198).
  * mode FL_MODE_COO: I, J (int32) and V have ndof^2*nelem entries, element-major, row-major within the element

@@ -253,11 +253,12 @@ def element_sorter(elements):
     return se, so
 
 
-def explicit_central_difference(T_of, X, M, F_ext_of, dt, nsteps, fixed_mask, applied_dirichlet_of=None, save_every=1):
+def explicit_central_difference(T_of, X, M, F_ext_of, dt, nsteps, fixed_mask, applied_dirichlet_of=None, save_every=1, contact_of=None):
     """Lumped-mass central-difference loop, mechanics only: numpy restatement of
     Florence/TimeIntegrators/ExplicitStructuralDynamicIntegrator.py:57-188 (zero initial U0, V0).
 
     T_of(Eulerx) -> internal force (nnode*ndim); F_ext_of(inc) -> nodal forces; fixed_mask bool (nnode*ndim).
+    contact_of(Eulerx) -> contact tractions added after every in-loop assembly (:190-197; not to the initial T).
     Returns (snapshots list of U arrays, final Eulerx, final T).
     """
     nnode, ndim = X.shape
@@ -286,6 +287,8 @@ def explicit_central_difference(T_of, X, M, F_ext_of, dt, nsteps, fixed_mask, ap
             snaps.append((U + inc_dir).copy())
         U00, U0 = U0, U                                  # :183-184
         T = T_of(Eulerx)                                 # :188
+        if contact_of is not None:
+            T = T + contact_of(Eulerx)                   # :190-197
     return snaps, Eulerx, T
 
 

@@ -1,0 +1,126 @@
+"""Rigid-plane penalty contact of the explicit solver: oracle vs the reference's golden vectors on CPU,
+device kernels vs both on the GPU, and the device-resident loop with contact against the oracle loop."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import contact as oc
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_contact.npz"))
+CASES = [("hex27", "hex", 2), ("quad4", "quad", 1)]
+
+
+def _g(tag):
+    return {k[len(tag) + 1:]: GOLD[k] for k in GOLD.files if k.startswith(tag + "_")}
+
+
+@pytest.mark.parametrize("tag,kind,p", CASES)
+def test_oracle_matches_reference_golden(tag, kind, p):
+    g = _g(tag)
+    T = oc.assemble_tractions(g["surface_nodes"], g["Eulerx"], g["normal"], float(g["distance"]), float(g["kappa"]), float(g["tol"]))
+    assert np.array_equal(T, g["T_contact"]) and np.abs(T).max() > 0
+    far = oc.assemble_tractions(g["surface_nodes"], g["Eulerx"], g["normal"], 50.0, float(g["kappa"]))
+    assert np.array_equal(far, g["T_far"]) and not far.any()
+
+
+def test_boundary_nodes_of_a_box():
+    from florence_b200 import mesh as flmesh
+    pts, els = flmesh.box_hex_mesh(3, 2, 2, p=2)
+    ids = flmesh.boundary_nodes(pts.numpy())
+    nx, ny, nz = 7, 5, 5
+    assert ids.shape[0] == nx * ny * nz - (nx - 2) * (ny - 2) * (nz - 2)
+    assert np.array_equal(ids, np.sort(ids))
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,kind,p", CASES)
+def test_device_contact_tractions(tag, kind, p):
+    import torch
+    from florence_b200 import backend, mesh as flmesh
+    g = _g(tag)
+    B, Jm, AG = flmesh.tables(kind, p)
+    dev = torch.device("cuda:0")
+    h = backend.AssemblyHandle(g["points"], g["elements"].astype(np.uint64), Jm, AG, B, device=dev)
+    h.set_contact(g["surface_nodes"], g["normal"], float(g["distance"]), float(g["kappa"]), float(g["tol"]))
+    x = torch.as_tensor(g["Eulerx"], device=dev)
+    T = h.assemble_contact(x).cpu().numpy()
+    ref = g["T_contact"]
+    # same contact set; values to rounding of the 2-3 term dot product (numpy's dot may fuse or reorder it)
+    assert np.array_equal(T != 0, ref != 0)
+    assert np.abs(T - ref).max() <= 4e-16 * np.abs(ref).max()
+    # accumulate mode adds to an existing force vector
+    base = torch.arange(T.size, dtype=torch.float64, device=dev)
+    acc = h.assemble_contact(x, out=base.clone(), accumulate=True).cpu().numpy()
+    assert np.array_equal(acc, base.cpu().numpy() + T)
+    # plane far away: no contact
+    h.set_contact(g["surface_nodes"], g["normal"], 50.0, float(g["kappa"]))
+    assert not h.assemble_contact(x).cpu().numpy().any()
+    # switched off: the stand-alone pass is a state error
+    h.set_contact(None, None, 0.0, 0.0)
+    with pytest.raises(Exception):
+        h.assemble_contact(x)
+    with pytest.raises(ValueError):
+        h.set_contact(np.array([10 ** 6]), g["normal"], 0.0, 1.0)
+    h.close()
+
+
+class _Contact(object):
+    def __init__(self, n, L, k, tol=1e-6):
+        self.plane_normal, self.distance, self.kappa, self.contact_gap_tolerance = np.asarray(n, float), L, k, tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,n", [(1, 4), (2, 2)])
+def test_explicit_loop_with_contact_against_oracle(p, n):
+    """A NeoHookean block thrown at a rigid wall: the device loop (contact inside the fused update kernel) follows the numpy
+    restatement of the reference loop step for step, and the wall actually pushes back."""
+    import torch
+    from florence_b200 import backend, mesh as flmesh, time_integrator
+    from oracle import oracle as orc
+    dev = torch.device("cuda:0")
+    pts, els = flmesh.box_hex_mesh(n, n, n, p=p)
+    B, Jm, AG = flmesh.tables("hex", p)
+    P, E = pts.numpy(), els.numpy()
+    nnode = P.shape[0]
+    surf = flmesh.boundary_nodes(P)
+    mu, lamb, rho = 4e5, 2e6, 1100.0
+    prm = orc.params(mu=mu, lamb=lamb)
+    h_el = 1.0 / (p * n)
+    dt = 0.2 * h_el / np.sqrt((lamb + 2 * mu) / rho)
+    nsteps = 60
+    fixed = np.zeros(nnode * 3, bool)
+    M = orc.assemble_mass(P, E, B, Jm, AG, 3, rho, "lumped")
+    # wall z = -0.002 (normal +z, gap = z + 0.002): a body force of 60 m/s^2 pushes the block onto it from step ~10 on;
+    # penalty stiffness at 5% of the explicit stability limit 4 m / dt^2 of the lightest node
+    contact = _Contact([0.0, 0.0, 1.0], 0.002, 0.05 * 4 * M.min() / dt ** 2)
+    fext = np.zeros((nnode, 3)); fext[:, 2] = -60.0 * M.reshape(nnode, 3)[:, 2]
+    T_of = lambda x: orc.assemble_explicit(P, E, x, None, Jm, AG, 3, prm, 1)
+    c_of = lambda x: oc.assemble_tractions(surf, x, contact.plane_normal, contact.distance, contact.kappa, contact.contact_gap_tolerance)
+    snaps, x_o, T_o = orc.explicit_central_difference(T_of, P, M, lambda inc: fext.ravel(), dt, nsteps, fixed, contact_of=c_of)
+    assert np.abs(c_of(x_o)).max() > 0 or any(np.abs(c_of(P + s.reshape(nnode, 3))).max() > 0 for s in snaps), "test never reaches the wall"
+
+    h = backend.AssemblyHandle(P, E, Jm, AG, B, device=dev)
+    mat = backend.make_material(1, rho, mu=mu, lamb=lamb)
+    integ = time_integrator.ExplicitStructuralDynamicIntegrator(h, mat, contact=contact, surface_nodes=surf)
+    assert np.abs(integ.M.cpu().numpy() - M).max() <= 1e-13 * M.max()
+    integ.initialise(P, fext.ravel(), fixed, dt)
+    f = torch.as_tensor(fext.ravel(), device=dev)
+    # single steps, compared with every oracle snapshot
+    for k, inc in enumerate(range(2, nsteps)):
+        assert integ.step(1, inc, f, 1.0, 0.0) == 0
+        U = integ.displacement().cpu().numpy().ravel()
+        assert np.abs(U - snaps[k]).max() <= 1e-9 * max(np.abs(snaps[k]).max(), 1e-12), inc
+    assert np.abs(integ.T.cpu().numpy() - T_o).max() <= 1e-8 * np.abs(T_o).max()
+    # one fused multi-step call gives the same trajectory bit for bit
+    integ2 = time_integrator.ExplicitStructuralDynamicIntegrator(h, mat, contact=contact, surface_nodes=surf)
+    integ2.initialise(P, fext.ravel(), fixed, dt)
+    assert integ2.step(nsteps - 2, 2, f, 1.0, 0.0) == 0
+    assert torch.equal(integ2.Eulerx, integ.Eulerx) and torch.equal(integ2.T, integ.T)
+    # without contact the block goes through the wall: the contact run must differ
+    integ3 = time_integrator.ExplicitStructuralDynamicIntegrator(h, mat)
+    integ3.initialise(P, fext.ravel(), fixed, dt)
+    integ3.step(nsteps - 2, 2, f, 1.0, 0.0)
+    assert float(integ3.Eulerx.view(-1, 3)[:, 2].min()) < float(integ.Eulerx.view(-1, 3)[:, 2].min())
+    h.close()
