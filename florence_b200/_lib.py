@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflorence_b200.so")
+# FL_B200_LIB: path of an alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("FL_B200_LIB") or os.path.join(_HERE, "libflorence_b200.so")
 
 FL_OK = 0
 FL_ERR_INVALID, FL_ERR_UNSUPPORTED, FL_ERR_CUDA, FL_ERR_STATE = -1, -2, -3, -4

@@ -15,6 +15,7 @@
 // written as contiguous (coalesced) segments and nothing is recomputed.  fp64 accumulators live in registers.
 #pragma once
 #include "fl_implicit_mma.cuh"
+#include "fl_implicit_warp.cuh"
 
 namespace fl {
 
@@ -314,7 +315,7 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                         for (int i = 0; i < D; ++i)
 #pragma unroll
                             for (int j = 0; j < D; ++j)
-                                Kb[i][j] = fma(prm.lamb, S[aa][i][j], prm.mu * S[aa][j][i]) + (i == j ? prm.mu * tr : 0.0);
+                                Kb[i][j] = __dadd_rn(fma(prm.lamb, S[aa][i][j], __dmul_rn(prm.mu, S[aa][j][i])), i == j ? __dmul_rn(prm.mu, tr) : 0.0);
 #pragma unroll
                         for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -540,6 +541,12 @@ int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, co
         // forced (option value 2): its 27 -> 32 tile padding makes the generic kernel the faster one
         if (h->use_mma_implicit == 2 && h->npe == 27 && h->ng == 27) return launch_impl_mma<MAT, 27, 27, 21>(h, Eulerx, Eulerp, prm, update, ke, te, st);
         if (h->use_mma_implicit && h->npe == 64 && h->ng == 64) return launch_impl_mma<MAT, 64, 64, 12>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+    }
+    if constexpr (D == 3 && MAT == MAT_LINEAR_ELASTIC) {
+        // tet10 / hex8 (8 Gauss points): warp-autonomous kernel, no block barriers, no staging tile (fl_implicit_warp.cuh)
+        const bool warp_ok = h->use_warp_iso && h->ng == 8 && (((size_t)ke) & 15) == 0;   // 16-byte stores
+        if (warp_ok && h->npe == 10) return launch_impl_iso_warp<10, 8>(h, Eulerx, prm, update, ke, te, st);
+        if (warp_ok && h->npe == 8) return launch_impl_iso_warp<8, 8>(h, Eulerx, prm, update, ke, te, st);
     }
     const int rows = h->npe / 2 + 1;
     if (rows <= 3) return launch_impl_A<D, MAT, 3>(h, Eulerx, Eulerp, prm, update, ke, te, st);

@@ -23,6 +23,12 @@ if n_tet:
         t = med(lambda: h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T)))
         print("tet10 %s implicit csr: nelem=%d elem=%.3f ms gather=%.3f ms T=%.3f ms -> %.1f Melem/s (elem kernel %.1f Melem/s)" %
               (name, els.shape[0], t[0], t[1], t[2], els.shape[0] / t.sum() / 1e3, els.shape[0] / t[0] / 1e3))
+        if num == 10:
+            h.set_option(2, 0)
+            V2, T2 = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+            t = med(lambda: h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V2, T2)))
+            print("   block-wide kernel (option 2 = 0): elem=%.3f ms; identical K: %s, identical T: %s" % (t[0], torch.equal(V, V2), torch.equal(T, T2)))
+            h.set_option(2, 1); del V2, T2
     h.close(); del V, T
 if n_hex:
     for p, n in ((2, n_hex), (1, 2 * n_hex)):
