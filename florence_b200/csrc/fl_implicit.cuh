@@ -544,7 +544,7 @@ int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, co
     }
     if constexpr (D == 3 && MAT == MAT_LINEAR_ELASTIC) {
         // tet10 / hex8 (8 Gauss points): warp-autonomous kernel, no block barriers, no staging tile (fl_implicit_warp.cuh)
-        const bool warp_ok = h->use_warp_iso && h->ng == 8 && (((size_t)ke) & 15) == 0;   // 16-byte stores
+        const bool warp_ok = h->use_warp_iso && h->ng == 8 && (((size_t)ke) & 31) == 0;   // 32-byte stores
         if (warp_ok && h->npe == 10) return launch_impl_iso_warp<10, 8>(h, Eulerx, prm, update, ke, te, st);
         if (warp_ok && h->npe == 8) return launch_impl_iso_warp<8, 8>(h, Eulerx, prm, update, ke, te, st);
     }

@@ -1,17 +1,21 @@
 // fl_implicit_warp.cuh -- warp-autonomous implicit element kernel for the isotropic constant-tangent material
-// (LinearElastic, _LinearElastic_.h:24-57) on small 3-D elements with 8 Gauss points (tet10, hex8: ndof <= 32).
+// (LinearElastic, _LinearElastic_.h:24-57) on small 3-D elements with 8 Gauss points and an even node count (tet10, hex8).
 //
 // Same arithmetic as the ISO path of implicit_elements_kernel (fl_implicit.cuh) -- K_ab = lamb S + mu S^T + mu tr(S) I with
-// S_ab = sum_g detJ grad N_a (x) grad N_b -- but organised so that one WARP carries a group of 32/NG elements through every
-// phase with __syncwarp only (the block-wide kernel idles at its five barriers, profiles/r1_summary.md):
+// S_ab = sum_g detJ grad N_a (x) grad N_b -- but organised so that one WARP carries a group of elements through every phase
+// with __syncwarp only (the block-wide kernel idles at its five barriers, profiles/r1_summary.md), and so that the shared
+// memory pipe, which bounds both kernels, moves as few wavefronts per element as possible:
 //   phase 1  lane = (element, Gauss point): kinematics, stress, spatial gradients -> shared memory
-//   phase 3  lane = (element, column node b): the lane owns the 3x3 blocks K_ab of its column node for every row node a.
-//            Its 8 x 3 weighted column gradients stay in registers, the row gradients are (per element) broadcast loads
-//            feeding 9 FMAs each -- a third of the shared-memory wavefronts of a lane-per-dof mapping -- and S^T, tr(S) are
-//            register-local.  The six K_e rows of a row-node pair (1440 contiguous bytes per element) pass through a small
-//            per-warp tile and leave as 16-byte, fully coalesced stores: 8-byte stores straight from the lanes fill a third
-//            of every 32-byte sector they touch and saturate the L1 -> crossbar write path (profiles/r2 notes).
-//   phase 4  lane = (element, node a): traction
+//   phase 3  lane = (element, PAIR of adjacent column nodes 2t, 2t+1).  The lane keeps the 8 x 6 weighted gradients of its
+//            two column nodes in registers and, per (row node a, Gauss point), reads the 3 gradient components of a once
+//            for 18 FMAs.  All lanes of a warp read at most EPW distinct addresses, one per element, placed 4 banks apart:
+//            every load is a conflict-free broadcast.  S^T and tr(S) are register-local.
+//            The three K_e rows of row node a (720 contiguous bytes per element) are written to a small per-warp tile
+//            (conflict-free 16-byte stores, 48 contiguous bytes per lane and row) and leave through the TMA engine
+//            (cp.async.bulk shared -> global, one copy per element and row node).  Stores issued from the lanes either
+//            fill a third to a half of each 32-byte sector (L1 -> crossbar write path saturates) or, staged and
+//            coalesced, cost the LSU data pipe -- the resource that bounds this kernel -- ~180 more wavefronts per element.
+//   phase 4  same lanes: traction of the two nodes
 // The next group's nodal coordinates are prefetched with cp.async while the current group is computed.
 #pragma once
 #include "fl_internal.cuh"
@@ -19,25 +23,25 @@
 namespace fl {
 
 #ifndef FL_IW_MINB
-#define FL_IW_MINB 3
-#endif
-#ifndef FL_IW_UNROLL_A
-#define FL_IW_UNROLL_A 1
+#define FL_IW_MINB 2
 #endif
 constexpr int IW_WARPS = 4;   // warps per block
 
 template <int NPE, int NG>
 struct iso_warp_shape {
     static constexpr int D = 3;
-    static constexpr int EPW = (32 / NG < 32 / NPE) ? 32 / NG : 32 / NPE;   // elements per warp group (tet10: 3, hex8: 4)
+    static constexpr int LPE = NPE / 2;              // lanes per element in phase 3 (one per node pair)
+    static constexpr int EPW = 32 / LPE;             // elements per warp group (tet10: 6, hex8: 8)
+    static constexpr int EPR = 32 / NG;              // elements per phase-1 round
+    static constexpr int ROUNDS = (EPW + EPR - 1) / EPR;
     static constexpr int NDOF = NPE * D;
     static constexpr int XS = NDOF | 1;              // per-element stride of the coordinate tiles
-    static constexpr int SGS = NDOF;                 // per-Gauss-point stride of the gradient tile (even: 16-byte row-pair loads)
-    static constexpr int SGE = NG * SGS + ((18 - (NG * SGS) % 16) % 16);   // per-element stride == 2 (mod 16): the elements of a
-                                                                          // group sit 4 banks apart, so their broadcasts never collide
+    static constexpr int SGS = NDOF | 1;             // per-Gauss-point stride of the gradient tile (odd: the phase-1 stores of
+                                                     // one element spread over distinct banks)
+    static constexpr int SGE = NG * SGS + ((25 - (NG * SGS) % 16) % 16);   // per-element stride == 9 (mod 16) doubles: the per-element
+                                                     // broadcast addresses of phase 3 fall into distinct banks (0,9,2,11,4,13,...)
     static constexpr int SSS = 9;                    // sigma * detJ
     static constexpr int SSE = NG * SSS + 1;         // per-element stride of the stress tile (distinct banks per element)
-    static constexpr int LDG = NG | 1;
     // per warp: 2 x (X, x) double-buffered, gradients, stresses, detJ
     static constexpr int X_OFF = 0;
     static constexpr int x_OFF = X_OFF + 2 * EPW * XS;
@@ -45,13 +49,15 @@ struct iso_warp_shape {
     static constexpr int SS_OFF = SG_OFF + EPW * SGE;
     static constexpr int DJ_OFF = SS_OFF + EPW * SSE;
     static constexpr int KT_OFF = (DJ_OFF + EPW * NG + 1) & ~1;
-    static constexpr int KTE = 2 * D * NDOF + 2;     // per-element stride of the K row-pair tile (6 rows of ndof doubles)
+    static constexpr int KTE = D * NDOF + ((30 - (D * NDOF) % 16) % 16);   // K row tile, per-element stride == 14 (mod 16) doubles:
+                                                     // the 16-byte stores of every quarter warp hit 8 distinct bank quads
     static constexpr int WARP_DOUBLES = KT_OFF + EPW * KTE;
+    static constexpr int LDG = NG | 1;
     static constexpr int JM_DOUBLES = D * NPE * LDG;
     static constexpr size_t SMEM = sizeof(double) * (JM_DOUBLES + NG + (size_t)IW_WARPS * WARP_DOUBLES);
-    static_assert(NG * EPW <= 32 && NPE * EPW <= 32 && EPW >= 1, "a group must fit a warp in both mappings");
-    static_assert(NPE % 2 == 0 && (JM_DOUBLES + NG) % 2 == 0 && SGE % 2 == 0 && SGS % 2 == 0 && (NDOF * NDOF) % 2 == 0 && KTE % 2 == 0,
-                  "row-pair loads and the 16-byte write-out need 16-byte alignment");
+    static_assert(NPE % 2 == 0 && LPE * EPW <= 32 && EPR >= 1, "a group must fit a warp");
+    static_assert((JM_DOUBLES + NG) % 2 == 0 && (NDOF * NDOF) % 2 == 0 && NDOF % 2 == 0 && KTE % 2 == 0 && (D * NDOF) % 2 == 0,
+                  "16-byte stores need 16-byte aligned rows");
 };
 
 template <int NPE, int NG>
@@ -60,7 +66,7 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
                          const double* __restrict__ jm_g, const double* __restrict__ gw_g, int64_t nelem, int ldg_g, int update,
                          MatParams prm, double* __restrict__ ke, double* __restrict__ te) {
     using S = iso_warp_shape<NPE, NG>;
-    constexpr int D = 3, EPW = S::EPW, NDOF = S::NDOF;
+    constexpr int D = 3, EPW = S::EPW, NDOF = S::NDOF, LPE = S::LPE;
     extern __shared__ __align__(16) double smem_w[];
     double* jm = smem_w;                     // [k][a][LDG]
     double* gw = jm + S::JM_DOUBLES;
@@ -106,15 +112,16 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
         asm volatile("cp.async.wait_all;");
         __syncwarp();
         if (grp + wstride < ngroups) gather(grp + wstride, buf ^ 1);
-        // ---- phase 1: lane = (element, Gauss point)
-        {
-            const int el = lane / NG, g = lane - el * NG;
-            const double* Xe = Xs0 + (buf * EPW + el) * S::XS;
-            const double* xe = xs0 + (buf * EPW + el) * S::XS;
-            double JX[9], Jx[9];
+        // ---- phase 1: lane = (element, Gauss point), EPR elements per round
+#pragma unroll 1
+        for (int round = 0; round < S::ROUNDS; ++round) {
+            const int el = round * S::EPR + lane / NG, g = lane % NG;
+            if (el < ne) {
+                const double* Xe = Xs0 + (buf * EPW + el) * S::XS;
+                const double* xe = xs0 + (buf * EPW + el) * S::XS;
+                double JX[9], Jx[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) JX[i] = Jx[i] = 0.0;
-            if (el < ne) {   // el >= EPW for the spare lanes of a 3-element group
+                for (int i = 0; i < 9; ++i) JX[i] = Jx[i] = 0.0;
 #pragma unroll
                 for (int a = 0; a < NPE; ++a) {
                     double j[D];
@@ -168,23 +175,22 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
             }
         }
         __syncwarp();
-        // ---- phase 3 / 4: lane = (element, node)
+        // ---- phase 3 / 4: lane = (element, node pair)
         {
-            const int el = lane / NPE, b = lane - el * NPE;
-            const bool act = el < ne;
+            const int el = lane / LPE, t = lane - el * LPE;
+            const bool act = el < ne;                // also false for the spare lanes (el >= EPW)
             const int elc = act ? el : 0;            // idle lanes shadow element 0 (loads only)
             const double* sge = SG + elc * S::SGE;
-            double bgv[NG][D];
+            double bgv[NG][2 * D];                   // weighted gradients of column nodes 2t, 2t+1
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const double d = dJ[elc * NG + g];
 #pragma unroll
-                for (int jj = 0; jj < D; ++jj) bgv[g][jj] = sge[g * S::SGS + b * D + jj] * d;
+                for (int c = 0; c < 2 * D; ++c) bgv[g][c] = sge[g * S::SGS + t * 2 * D + c] * d;
             }
-            // two row nodes per trip: their 6 gradient components are three 16-byte loads
-            constexpr int UA = FL_IW_UNROLL_A;
-#pragma unroll(UA)
-            for (int a2 = 0; a2 < NPE / 2; ++a2) {
+            double* ktl = KT + elc * S::KTE + t * 2 * D;
+#pragma unroll 1
+            for (int a = 0; a < NPE; ++a) {
                 double Sm[2][D][D];
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
@@ -194,65 +200,81 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
                         for (int jj = 0; jj < D; ++jj) Sm[q][i][jj] = 0.0;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const double2* ap2 = reinterpret_cast<const double2*>(sge + g * S::SGS + a2 * 2 * D);
-                    const double2 p0 = ap2[0], p1 = ap2[1], p2 = ap2[2];
-                    const double ap[2 * D] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};
+                    const double* ap = sge + g * S::SGS + a * D;
 #pragma unroll
-                    for (int q = 0; q < 2; ++q)
+                    for (int i = 0; i < D; ++i) {
+                        const double ai = ap[i];
 #pragma unroll
-                        for (int i = 0; i < D; ++i)
+                        for (int q = 0; q < 2; ++q)
 #pragma unroll
-                            for (int jj = 0; jj < D; ++jj) Sm[q][i][jj] = fma(ap[q * D + i], bgv[g][jj], Sm[q][i][jj]);
+                            for (int jj = 0; jj < D; ++jj) Sm[q][i][jj] = fma(ai, bgv[g][q * D + jj], Sm[q][i][jj]);
+                    }
                 }
+                double tr[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    double tr = 0;
+                    tr[q] = 0;
 #pragma unroll
-                    for (int i = 0; i < D; ++i) tr += Sm[q][i][i];
-                    double* kt = KT + elc * S::KTE + (q * D) * NDOF + b * D;
-                    if (act) {
+                    for (int i = 0; i < D; ++i) tr[q] += Sm[q][i][i];
+                }
+                // the previous row block must have been read out of the tile before it is overwritten
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                if (act) {
 #pragma unroll
-                        for (int i = 0; i < D; ++i)
+                    for (int i = 0; i < D; ++i) {
+                        double kv[2 * D];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
 #pragma unroll
                             for (int jj = 0; jj < D; ++jj)
-                                kt[i * NDOF + jj] =
-                                    __dadd_rn(fma(prm.lamb, Sm[q][i][jj], __dmul_rn(prm.mu, Sm[q][jj][i])), i == jj ? __dmul_rn(prm.mu, tr) : 0.0);
+                                kv[q * D + jj] = __dadd_rn(fma(prm.lamb, Sm[q][i][jj], __dmul_rn(prm.mu, Sm[q][jj][i])),
+                                                           i == jj ? __dmul_rn(prm.mu, tr[q]) : 0.0);
+                        double2* row = reinterpret_cast<double2*>(ktl + i * NDOF);
+                        row[0] = make_double2(kv[0], kv[1]);
+                        row[1] = make_double2(kv[2], kv[3]);
+                        row[2] = make_double2(kv[4], kv[5]);
                     }
                 }
+                // rows 3a .. 3a+2 of each element (720 contiguous bytes in the tile and in K_e) leave through the TMA engine:
+                // one bulk shared -> global copy per element, issued by one lane; the LSU data pipe never sees them
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                // rows 6 a2 .. 6 a2 + 5 of every element of the group: D * NDOF double2 per element, contiguous in K_e
-                {
-                    constexpr int PER = D * NDOF;          // double2 per element
-                    double2* dst = reinterpret_cast<double2*>(ke + (size_t)e0 * NDOF * NDOF + (size_t)a2 * 2 * D * NDOF);
-                    for (int f = lane; f < ne * PER; f += 32) {
-                        const int el2 = f / PER, r = f - el2 * PER;
-                        dst[(size_t)el2 * (NDOF * NDOF / 2) + r] = reinterpret_cast<const double2*>(KT + el2 * S::KTE)[r];
-                    }
+                if (lane < ne) {
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(KT + lane * S::KTE);
+                    double* dst = ke + (size_t)(e0 + lane) * NDOF * NDOF + (size_t)a * D * NDOF;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(D * NDOF * 8) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                __syncwarp();
             }
             // traction t_b = sum_g grad N_b . (sigma detJ)   (only when the geometry is updated, _LowLevelAssemblyDF_.h:136-148)
             if (act) {
-                double t[D];
+                double tv[2 * D];
 #pragma unroll
-                for (int i = 0; i < D; ++i) t[i] = 0.0;
+                for (int c = 0; c < 2 * D; ++c) tv[c] = 0.0;
                 if (update == 1) {
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        const double* ag = sge + g * S::SGS + b * D;
                         const double* So = Ss + el * S::SSE + g * S::SSS;
 #pragma unroll
-                        for (int i = 0; i < D; ++i)
+                        for (int q = 0; q < 2; ++q) {
+                            const double* ag = sge + g * S::SGS + (2 * t + q) * D;
 #pragma unroll
-                            for (int l = 0; l < D; ++l) t[i] = fma(ag[l], l <= i ? So[l * D + i] : So[i * D + l], t[i]);
+                            for (int i = 0; i < D; ++i)
+#pragma unroll
+                                for (int l = 0; l < D; ++l) tv[q * D + i] = fma(ag[l], l <= i ? So[l * D + i] : So[i * D + l], tv[q * D + i]);
+                        }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < D; ++i) te[((e0 + el) * NPE + b) * D + i] = t[i];
+                double2* trow = reinterpret_cast<double2*>(te + ((e0 + el) * NPE + 2 * t) * D);
+                trow[0] = make_double2(tv[0], tv[1]);
+                trow[1] = make_double2(tv[2], tv[3]);
+                trow[2] = make_double2(tv[4], tv[5]);
             }
         }
         __syncwarp();
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int NPE, int NG>
