@@ -6,7 +6,7 @@ elements, 1 367 631 nodes, implicit stiffness + residual assembled to CSR (requi
 computed).  One "step" = one full assembly (K values in CSR order + T) of the whole mesh.
   value : elements/s with the state already in HBM (CUDA events around K steps, max over ranks)
   e2e   : the same assembly through the reference-facing plug-in function with HOST numpy state in and HOST K values / T out
-  roofline / roofline_fp64 : dominant kernel (implicit_elements_kernel) timed with CUDA events inside the library
+  roofline / roofline_fp64 : dominant kernel by share of the step (CUDA events inside the library), the other kernels and the whole step
   cpu_baseline : the CPU restatement of the reference algorithm (oracle, -O3 -ffast-math) on a bounded sample, 1 core
   explicit : secondary line for the metric's second half -- NeoHookean p=2 hex explicit dynamics, DOF-updates/s
 N > 1 (torchrun): weak scaling, every rank assembles its own slab (+1 halo layer of elements so the CSR rows of the nodes it
@@ -289,24 +289,44 @@ def run_b200(args, rank, world, local_rank):
     # B = 8 npe + (nnode/nelem)(2*8*d) + (nnode/nelem) 8 nvar + 4 ndof^2 + 8 nnz/nelem
     B_alg = 8 * 10 + nnode_per_elem * (2 * 8 * 3) + nnode_per_elem * 8 * 3 + 4 * ndof * ndof + 8.0 * nnz / nelem_local
     Fl_ref = 8 * (10 * 9 * 10 + 100 + 150 + (2 * 30 * 6 + 2 * 30)) + 8 * (2 * 36 * 30 + 2 * 6 * 900 + 2 * 900 + 25 * 100)
-    achieved_gbs = B_alg * nelem_local / (k_elem * 1e-3) / 1e9
     dfma = backend.measure_fp64_peak(False, 20000)
     launches += 4
-    roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None,
-            "kernel": "implicit_elements_kernel<3,LinearElastic,10>", "kernel_ms": float(k_elem), "peak_source": peak_src,
-            "algorithmic_bytes_per_element": B_alg, "share_of_step": float(k_elem / (k_elem + k_csr + k_T)),
-            "other_kernels_ms": {"csr_gather_kernel": float(k_csr), "gather_nodes_kernel": float(k_T)}}
+    traffic = {}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get("implicit_elements_kernel_bytes_per_launch")
+            traffic = json.load(open(tr))
         except Exception:
-            pass
+            traffic = {}
+    k_step = k_elem + k_csr + k_T
+    # per-kernel algorithmic bytes per element.  Element kernel: SURVEY.md 8(d)'s whole-path figure B (state in, K values out).
+    # CSR reduction: what it has to move in this design -- the K_e rows it sums (8 ndof^2), the uint16 rank map (2 npe^2) and the
+    # CSR values it writes (8 nnz/nelem).
+    B_csr = 8.0 * ndof * ndof + 2.0 * 10 * 10 + 8.0 * nnz / nelem_local
+    kernels = {
+        "implicit_iso_warp_kernel<10,8>": {"ms": float(k_elem), "bytes_per_element": B_alg, "traffic_key": "implicit_iso_warp_kernel_bytes_per_launch"},
+        "csr_gather_kernel<3,10>": {"ms": float(k_csr), "bytes_per_element": B_csr, "traffic_key": "csr_gather_kernel_bytes_per_launch"},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    def _roof(name):
+        kk = kernels[name]
+        ach = kk["bytes_per_element"] * nelem_local / (kk["ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get(kk["traffic_key"]),
+                "kernel": name, "kernel_ms": kk["ms"], "algorithmic_bytes_per_element": kk["bytes_per_element"],
+                "share_of_step": kk["ms"] / k_step}
+    roof = _roof(dom)
+    roof["peak_source"] = peak_src
+    roof["other_kernels"] = [_roof(k) for k in kernels if k != dom] + [{"kernel": "gather_nodes_kernel<3>", "kernel_ms": float(k_T)}]
+    # the whole step against the same roofline: SURVEY 8(d)'s compulsory bytes over all three kernels
+    roof["step"] = {"achieved": B_alg * nelem_local / (k_step * 1e-3) / 1e9, "frac": B_alg * nelem_local / (k_step * 1e-3) / 1e9 / hbm_peak,
+                    "ms": float(k_step), "algorithmic_bytes_per_element": B_alg}
     # executed fp64 work of the element kernel (LinearElastic takes the isotropic constant-tangent path):
-    # kinematics 8 gp x (18 npe + ~120) + spatial gradients 8*10*9 + S_ab 8 gp x 60 node pairs x 9 + combination + traction
-    Fl_exec = 2.0 * (8 * (18 * 10 + 120) + 8 * 10 * 9 + 8 * 60 * 9 + 60 * 15 + 8 * 10 * 9)
+    # kinematics 8 gp x (18 npe + ~120) + spatial gradients 8*10*9 + S_ab 8 gp x 100 node pairs x 9 (the warp-autonomous kernel
+    # computes every block, no symmetry) + traction, FMA = 2; + the combination lamb S + mu S^T + mu tr I (~30 per node pair)
+    Fl_exec = 2.0 * (8 * (18 * 10 + 120) + 8 * 10 * 9 + 8 * 100 * 9 + 8 * 10 * 9) + 100 * 30
     roof64 = {"bound": "fp64", "achieved": Fl_exec * nelem_local / (k_elem * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
               "frac": Fl_exec * nelem_local / (k_elem * 1e-3) / 1e12 / dfma, "flops_per_element_executed": Fl_exec,
+              "kernel": "implicit_iso_warp_kernel<10,8>", "kernel_ms": float(k_elem),
               "reference_count": {"flops_per_element": Fl_ref, "equivalent_tflops": Fl_ref * nelem_local / (k_elem * 1e-3) / 1e12,
                                   "note": "what the reference's dense dgemm formulation would need for the same result (SURVEY.md 8d)"},
               "peak_source": "measured in this run (fl_measure_fp64_peak, register-resident DFMA loop)"}

@@ -261,6 +261,8 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
                 sgo[k] = v;
             }
         }
+        // the previous batch's bulk copy must have read the staging tile before phase 3 overwrites it
+        if (STAGE && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
         // ---- phase 3 (isotropic constant tangent): S_ab = sum_g detJ grad N_a (x) grad N_b for column node b and AI row nodes
         if constexpr (ISO) {
@@ -461,11 +463,21 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             for (int i = 0; i < NV; ++i) te[(e0 * npe + it) * NV + i] = t[i];
         }
         if (STAGE) {
-            // ---- phase 5: stream the staged element matrices of this batch out as one contiguous, fully coalesced run
-            __syncthreads();
+            // ---- phase 5: the staged element matrices of this batch are one contiguous run in K_e: hand them to the TMA engine
+            //      (one bulk shared -> global copy issued by thread 0) so that neither the tile read nor the global stores pass
+            //      through the LSU data pipe, which bounds this kernel.  Odd-sized / misaligned runs take the 16-byte store loop.
             double* dst = ke + (size_t)e0 * ndof * ndof;
             const int tot = ne * ndof * ndof;
-            if ((((size_t)dst) & 15) == 0) {
+            const bool bulk = ((((size_t)dst) & 15) == 0) && ((tot & 1) == 0);
+            if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (bulk) {
+                if (threadIdx.x == 0) {
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(Kst);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(tot * 8) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if ((((size_t)dst) & 15) == 0) {
                 double2* d2 = reinterpret_cast<double2*>(dst);
                 const double2* s2 = reinterpret_cast<const double2*>(Kst);
                 for (int t = threadIdx.x; t < tot / 2; t += blockDim.x) d2[t] = s2[t];
@@ -475,6 +487,7 @@ implicit_elements_kernel(const int32_t* __restrict__ conn, const double* __restr
             }
         }
     }
+    if (STAGE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int D, int MAT, int A, int SYM, int JM_SMEM, int NPE_T, int NG_T, int MINB, int STAGE>
