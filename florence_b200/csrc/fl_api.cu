@@ -316,11 +316,15 @@ int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Euler
         if (rc) return rc;
         ke = h->ke;
     }
+    // CSR mode with the DMMA kernel of p = 3 hexahedra: the K_e scratch is laid out as dof-pair planes (full-sector fragment stores);
+    // the wide CSR reduction reads the same layout.  COO mode always keeps the reference's element-major triplet order.
+    h->ke_plane_major = (mode == FL_MODE_CSR && h->ndim == 3 && h->use_mma_implicit && h->npe == 64 && h->ng == 64) ? 1 : 0;
     mark(h, 0, st);
     rc = launch_implicit_elements(h, Eulerx, Eulerp, mat, formulation_number, requires_geometry_update ? 1 : 0, ke, h->te, st);
     if (rc) return rc;
     mark(h, 1, st);
     rc = scatter_stiffness(h, nvar, mode, ke, I, J, V, st);
+    h->ke_plane_major = 0;
     if (rc) return rc;
     mark(h, 2, st);
     rc = launch_gather_nodes(h, nvar, h->te, T, st);
@@ -331,6 +335,7 @@ int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Euler
 int fl_assemble_laplacian(fl_handle* h, const double* e_tensor_host, int is_hessian_symmetric, int mode, int32_t* I, int32_t* J, double* V,
                           void* stream) {
     if (!h || !e_tensor_host || !V) { set_error("null argument"); return FL_ERR_INVALID; }
+    h->ke_plane_major = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == FL_MODE_CSR && !h->pat.nbr_ptr) { set_error("CSR assembly requires fl_pattern_build first"); return FL_ERR_STATE; }
     // the d x d tensor rides in the traction scratch buffer
@@ -351,6 +356,7 @@ int fl_assemble_laplacian(fl_handle* h, const double* e_tensor_host, int is_hess
 int fl_assemble_mass(fl_handle* h, double rho, int nvar, int mass_type, int mode, double* mass, int32_t* I, int32_t* J, double* V,
                      void* stream) {
     if (!h || nvar < 1 || nvar > 4) { set_error("bad argument"); return FL_ERR_INVALID; }
+    h->ke_plane_major = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ndof = (size_t)h->npe * nvar;
     if (mass_type == 0) {

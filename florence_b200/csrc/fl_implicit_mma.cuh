@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(IMMA_THREADS, 1)
 implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                              const double* __restrict__ phi, const double* __restrict__ jm, const double* __restrict__ jmT,
                              const double* __restrict__ gw, int64_t nelem, int ldg, int update, MatParams prm,
-                             double* __restrict__ ke, double* __restrict__ te) {
+                             double* __restrict__ ke, double* __restrict__ te, int plane_major) {
     constexpr int D = 3;
     constexpr bool EL = mat_traits<MAT>::electro;
     constexpr bool GEO = mat_traits<MAT>::geometric;
@@ -269,8 +269,15 @@ implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
                                 for (int z = 0; z < 2; ++z) {
                                     const int b = 8 * q + 2 * lc + z;
                                     if (b < NPE) {
-                                        Ke[(size_t)(a * NV + i) * ndof + b * NV + j] = c[m][q][z];
-                                        if (i != j) Ke[(size_t)(b * NV + j) * ndof + a * NV + i] = c[m][q][z];
+                                        if (plane_major) {
+                                            // K_e scratch as dof-pair planes [(i,j)][a][b]: the 4 lanes of a fragment row write 64
+                                            // contiguous bytes, and so do the 8 lanes of a fragment column in the mirror plane
+                                            Ke[((size_t)(i * NV + j) * NPE + a) * NPE + b] = c[m][q][z];
+                                            if (i != j) Ke[((size_t)(j * NV + i) * NPE + b) * NPE + a] = c[m][q][z];
+                                        } else {
+                                            Ke[(size_t)(a * NV + i) * ndof + b * NV + j] = c[m][q][z];
+                                            if (i != j) Ke[(size_t)(b * NV + j) * ndof + a * NV + i] = c[m][q][z];
+                                        }
                                     }
                                 }
                         }
@@ -294,7 +301,7 @@ int launch_impl_mma(fl_handle* h, const double* Eulerx, const double* Eulerp, co
     if (occ < 1) occ = 1;
     const int grid = (int)(h->nelem < (int64_t)occ * h->sm_count ? h->nelem : (int64_t)occ * h->sm_count);
     if (grid == 0) return FL_OK;
-    kern<<<grid, IMMA_THREADS, S::SMEM, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->jmT, h->gw, h->nelem, h->ldg, update, prm, ke, te);
+    kern<<<grid, IMMA_THREADS, S::SMEM, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->jmT, h->gw, h->nelem, h->ldg, update, prm, ke, te, h->ke_plane_major);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }

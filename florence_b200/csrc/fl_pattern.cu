@@ -354,7 +354,8 @@ csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict
 template <int NV>
 __global__ void __launch_bounds__(256)
 csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
-                       const uint16_t* __restrict__ rank, const double* __restrict__ ke, int64_t nnode, int npe, double* __restrict__ V) {
+                       const uint16_t* __restrict__ rank, const double* __restrict__ ke, int64_t nnode, int npe, int plane_major,
+                       double* __restrict__ V) {
     extern __shared__ double rowbuf[];
     const int ndof = npe * NV;
     const int run = NV * ndof;
@@ -370,10 +371,20 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
             const int a = (int)(flat - e * npe);
             const uint16_t* rk = rank + flat * npe;
             const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof;
-            for (int t = threadIdx.x; t < run; t += blockDim.x) {
-                const int i = t / ndof, c = t - i * ndof;
-                const int b = c / NV, l = c - b * NV;
-                rowbuf[i * w + (int)rk[b] * NV + l] += krow[t];
+            if (plane_major) {
+                // K_e scratch stored as dof-pair planes [(i,l)][a][b] (DMMA element kernels): npe-long contiguous runs
+                const double* kel = ke + e * (int64_t)ndof * ndof + (int64_t)a * npe;
+                for (int t = threadIdx.x; t < run; t += blockDim.x) {
+                    const int il = t / npe, b = t - il * npe;
+                    const int i = il / NV, l = il - i * NV;
+                    rowbuf[i * w + (int)rk[b] * NV + l] += kel[(int64_t)il * npe * npe + b];
+                }
+            } else {
+                for (int t = threadIdx.x; t < run; t += blockDim.x) {
+                    const int i = t / ndof, c = t - i * ndof;
+                    const int b = c / NV, l = c - b * NV;
+                    rowbuf[i * w + (int)rk[b] * NV + l] += krow[t];
+                }
             }
             __syncthreads();
         }
@@ -398,7 +409,7 @@ static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cud
     int64_t blocks = h->nnode;
     const int64_t cap = (int64_t)h->sm_count * occ * 8;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, V);
+    kern<<<(unsigned)blocks, 256, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, h->ke_plane_major, V);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }
