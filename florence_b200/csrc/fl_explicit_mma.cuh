@@ -83,10 +83,12 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
         for (int q = 0; q < GI; ++q) {
             const int it = threadIdx.x + q * MMA_THREADS;
             if (it < NE * NPE) {
-                const int el = it / NPE, a = it - el * NPE;
+                // element index fastest: the lanes of a warp write one tile row (stride 6 doubles), not one tile column
+                // (stride LDX == 8 mod 16, a 16-way bank conflict on every cp.async)
+                const int a = it / NE, el = it - a * NE;
                 double* d = dstb + a * S::LDX + el * 6;
                 if (el < nb) {
-                    const int64_t n = conn[b0 * NPE + it];
+                    const int64_t n = conn[(b0 + el) * NPE + a];
                     const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
 #pragma unroll
                     for (int l = 0; l < 3; ++l) {
@@ -148,7 +150,8 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
         __syncthreads();
         // ---- kinematics + constitutive law at (element, Gauss point)
         for (int it = threadIdx.x; it < NE * NG; it += MMA_THREADS) {
-            const int el = it / NG, g = it - el * NG;
+            // element index fastest: a warp reads / writes along tile rows (the P stores were a 16-way conflict column-wise)
+            const int g = it / NE, el = it - g * NE;
             double Pv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (el < ne) {
                 double JX[9], Jx[9];
