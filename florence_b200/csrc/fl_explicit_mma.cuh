@@ -25,8 +25,11 @@ struct mma_shape {
     static constexpr int M3 = NPE, K3 = 3 * NG, N3 = 3 * NE;
     static constexpr int MT1 = (M1 + 7) / 8, KS1 = (K1 + 3) / 4, NT1 = N1 / 8;
     static constexpr int MT3 = (M3 + 7) / 8, KS3 = (K3 + 3) / 4, NT3 = N3 / 8;
-    // leading dimensions == 8 (mod 16): the four 64-byte row segments of a B fragment tile two 128-byte wavefronts exactly
-    static constexpr int LDX = N1 + 8, LDP = N3 % 16 == 8 ? N3 : N3 + 8, LDJ = NPE > 8 ? N1 + 1 : N1 + 2;  // hex27: 3 blocks/SM need the smaller tile; hex8 keeps 16-byte aligned rows
+    // B-fragment tiles: lane 4 n + k reads [k][n], and a 64-bit shared load is served per half warp (n = 0..3 | 4..7, k = 0..3),
+    // so the leading dimension must be == 4 or 12 (mod 16) doubles for the 16 addresses to fall into 16 distinct banks
+    // (== 8, the rule for 32-bit fragments, is a 2-way conflict here: ncu showed 4 wavefronts per LDS.64 instead of 2)
+    static constexpr int pad_b(int n) { return ((4 - n % 16) + 16) % 16 < ((12 - n % 16) + 16) % 16 ? ((4 - n % 16) + 16) % 16 : ((12 - n % 16) + 16) % 16; }
+    static constexpr int LDX = N1 + pad_b(N1), LDP = N3 + pad_b(N3), LDJ = NPE > 8 ? N1 + 1 : N1 + 2;  // hex27: 3 blocks/SM need the smaller tile; hex8 keeps 16-byte aligned rows
     static constexpr int XX_SZ = KS1 * 4 * LDX, JAC_SZ = MT1 * 8 * LDJ, P_SZ = KS3 * 4 * LDP, TE_SZ = NE * NPE * 3;
     static constexpr int SCR_SZ = JAC_SZ > TE_SZ ? JAC_SZ : TE_SZ;  // te staging aliases the Jacobian tile
     static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * XX_SZ + SCR_SZ + P_SZ);  // coordinates are double-buffered
@@ -75,20 +78,30 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
     for (int i = threadIdx.x; i < S::P_SZ; i += MMA_THREADS) Ps[i] = 0.0;
 
     // Asynchronous gather (cp.async, 8 bytes per coordinate) of the [X | x] tile of a batch into buffer `buf`:
-    // XX[a][e*6 + c].  Elements beyond the end of the mesh are zero-filled.
-    auto gather = [&](int64_t b0, int buf) {
-        double* dstb = XXs + buf * S::XX_SZ;
+    // XX[a][e*6 + c].  Elements beyond the end of the mesh are zero-filled.  The connectivity entries of the batch were loaded
+    // into registers one iteration earlier (load_conn), so the cp.async addresses never wait on a global load.
+    int32_t cn[GI];
+    auto load_conn = [&](int64_t b0) {
         const int nb = (int)min((int64_t)NE, nelem - b0);
+#pragma unroll
+        for (int q = 0; q < GI; ++q) {
+            const int it = threadIdx.x + q * MMA_THREADS;
+            const int a = it / NE, el = it - a * NE;
+            cn[q] = (it < NE * NPE && el < nb) ? conn[(b0 + el) * NPE + a] : -1;
+        }
+    };
+    auto gather = [&](int buf) {
+        double* dstb = XXs + buf * S::XX_SZ;
 #pragma unroll
         for (int q = 0; q < GI; ++q) {
             const int it = threadIdx.x + q * MMA_THREADS;
             if (it < NE * NPE) {
                 // element index fastest: the lanes of a warp write one tile row (stride 6 doubles), not one tile column
-                // (stride LDX == 8 mod 16, a 16-way bank conflict on every cp.async)
+                // (stride LDX, a 16-way bank conflict on every cp.async)
                 const int a = it / NE, el = it - a * NE;
                 double* d = dstb + a * S::LDX + el * 6;
-                if (el < nb) {
-                    const int64_t n = conn[(b0 + el) * NPE + a];
+                if (cn[q] >= 0) {
+                    const int64_t n = cn[q];
                     const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
 #pragma unroll
                     for (int l = 0; l < 3; ++l) {
@@ -106,7 +119,11 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
 
     const int64_t nbatch = (nelem + NE - 1) / NE;
     __syncthreads();
-    if ((int64_t)blockIdx.x < nbatch) gather((int64_t)blockIdx.x * NE, 0);
+    if ((int64_t)blockIdx.x < nbatch) {
+        load_conn((int64_t)blockIdx.x * NE);
+        gather(0);
+        if ((int64_t)blockIdx.x + gridDim.x < nbatch) load_conn(((int64_t)blockIdx.x + gridDim.x) * NE);
+    }
     int buf = 0;
     for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x, buf ^= 1) {
         const int64_t e0 = batch * NE;
@@ -114,8 +131,11 @@ explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
         const double* XXc = XXs + buf * S::XX_SZ;
         asm volatile("cp.async.wait_all;");
         __syncthreads();   // coordinates of this batch have landed; previous batch's write-out is finished
-        // prefetch the next batch while this one is computed
-        if (batch + gridDim.x < nbatch) gather((batch + gridDim.x) * NE, buf ^ 1);
+        // prefetch the next batch's coordinates while this one is computed, and the connectivity of the one after
+        if (batch + gridDim.x < nbatch) {
+            gather(buf ^ 1);
+            if (batch + 2 * (int64_t)gridDim.x < nbatch) load_conn((batch + 2 * (int64_t)gridDim.x) * NE);
+        }
         // ---- GEMM 1: Jacobians.  NB1 n-tiles are accumulated together so MTW1*NB1 independent DMMA chains are in flight.
 #pragma unroll 1
         for (int jn = 0; jn < NTW1; jn += NB1) {

@@ -25,7 +25,7 @@ struct imma_shape {
     static constexpr int C3 = 3 * NV;                       // rows/cols of Chat_g
     static constexpr int MT = (NPE + 7) / 8, NT = (NPE + 7) / 8, KS = (3 * NG + 3) / 4;
     static constexpr int NCH = (KS + KC - 1) / KC;          // K chunks
-    static constexpr int LDW = NT * 8 + 8;                  // == 8 (mod 16)
+    static constexpr int LDW = NT * 8 + 4;                  // == 4 (mod 16): conflict-free 64-bit B-fragment loads (see fl_explicit_mma.cuh)
     static constexpr int CH_SZ = NG * C3 * C3, W_SZ = KC * 4 * LDW, XX_SZ = NPE * 7, P_SZ = NG * C3;
     static constexpr size_t SMEM = sizeof(double) * (size_t)(CH_SZ + 2 * W_SZ + XX_SZ + P_SZ);
 };
