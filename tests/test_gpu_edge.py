@@ -98,3 +98,39 @@ def test_invalid_inputs_raise():
     with pytest.raises(ValueError):
         h.assemble_laplacian(np.eye(2))
     h.close()
+
+
+@pytest.mark.parametrize("kind,p,nel", [("tet", 2, 1), ("tet", 2, 5), ("tet", 2, 6), ("tet", 2, 7), ("tet", 2, 13), ("tet", 2, 48),
+                                        ("hex", 1, 1), ("hex", 1, 7), ("hex", 1, 8), ("hex", 1, 9), ("hex", 1, 27)])
+def test_warp_autonomous_kernel_ragged_groups(kind, p, nel):
+    """LinearElastic tet10 / hex8 take the warp-autonomous kernel (groups of 6 / 8 elements per warp, TMA bulk stores of the
+    K_e rows): element counts around the group size, both detJ rules, COO and CSR, against the oracle and against the
+    block-wide kernel (fl_set_option 2)."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    n = 2 if kind == "tet" else 3
+    pts, els = (flmesh.box_tet_mesh if kind == "tet" else flmesh.box_hex_mesh)(n, n, n, p=p)
+    pts, els = pts.numpy(), els.numpy()[:nel]
+    B, Jm, AG = flmesh.tables(kind, p)
+    x = pts + 0.02 / (p * n) * np.sin(7 * pts + 1.0)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, B)
+    mat = backend.make_material(10, 1.0, mu=3.0, lamb=7.0)
+    prm = orc.params(mu=3.0, lamb=7.0)
+    pat = orc.sparsity_pattern(els, pts.shape[0], 3)
+    h.build_pattern(3)
+    for update in (True, False):
+        Vo, To = orc.assemble_implicit(pts, els, x, None, Jm, AG, 3, 6, int(update), prm, 10, mode="csr", pattern=pat)
+        res = {}
+        for opt in (1, 0):
+            h.set_option(2, opt)
+            V, T = h.assemble_implicit(x, None, mat, 0, update, mode="csr")
+            I, J, Vc, Tc = h.assemble_implicit(x, None, mat, 0, update, mode="coo")
+            res[opt] = (V.cpu().numpy(), T.cpu().numpy(), Vc.cpu().numpy())
+            assert np.abs(res[opt][0] - Vo).max() <= 1e-10 * np.abs(Vo).max()
+            assert np.abs(res[opt][1] - To).max() <= 1e-11 * max(np.abs(To).max(), 1e-300)
+            assert torch.equal(T, Tc)
+        assert np.abs(res[1][0] - res[0][0]).max() <= 1e-13 * np.abs(Vo).max()
+        assert np.abs(res[1][2] - res[0][2]).max() <= 1e-13 * np.abs(Vo).max()
+        assert np.array_equal(res[1][1], res[0][1])
+    h.set_option(2, 1)
+    h.close()
