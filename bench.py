@@ -406,7 +406,7 @@ def run_b200(args, rank, world, local_rank):
                             "config": {"workload": "hex27 NeoHookean explicit central difference, %d^3 elements per GPU" % ne, "ndof": ndof_global,
                                        "interface_bytes_per_step": 0 if ex is None else ex.bytes_per_exchange()},
                             "roofline": {"bound": "hbm", "achieved": B_x * nel / (t_el * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                         "frac": B_x * nel / (t_el * 1e-3) / 1e9 / hbm_peak, "kernel": "explicit_elements_kernel<3,NeoHookean>",
+                                         "frac": B_x * nel / (t_el * 1e-3) / 1e9 / hbm_peak, "kernel": "explicit_elements_mma_kernel<NeoHookean,27,27,8>",
                                          "kernel_ms": t_el, "gather_ms": t_g},
                             "roofline_fp64": {"achieved": Fl_x_exec * nel / (t_el * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
                                               "frac": Fl_x_exec * nel / (t_el * 1e-3) / 1e12 / dfma, "flops_per_element_executed": Fl_x_exec,

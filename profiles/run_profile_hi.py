@@ -12,7 +12,8 @@ phi = 9e3 * pts[:, 2] + 10.0 * (2 * torch.rand(pts.shape[0], dtype=torch.float64
 h = backend.AssemblyHandle(pts, els, Jm, AG, B, device=dev)
 mu = 5e4; lamb = 2 * mu * 0.4 / (1 - 0.8)
 mat = backend.make_material(8, 1200.0, mu1=mu, mu2=mu, lamb=lamb, eps_2=4 * 8.8541e-12)
+h.build_pattern(4)
 for _ in range(3):
-    I, J, V, T = h.assemble_implicit(x, phi, mat, 1, True, mode="coo", with_indices=False)
+    V, T = h.assemble_implicit(x, phi, mat, 1, True, mode="csr")
 torch.cuda.synchronize()
 print("done")
