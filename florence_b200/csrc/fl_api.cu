@@ -186,7 +186,7 @@ int fl_destroy(fl_handle* h) {
     if (!h) return FL_OK;
     for (int k = 0; k < 4; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->jmT); cudaFree(h->bases); cudaFree(h->gw);
-    cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank);
+    cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank); cudaFree(h->pat.rank_adj);
     dirichlet_free(h);
     cudaFree(h->contact.surf);
     cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag);

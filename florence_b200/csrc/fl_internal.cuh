@@ -29,6 +29,7 @@ struct Pattern {
     int64_t* nbr_ptr = nullptr;  // nnode+1
     int32_t* nbr_idx = nullptr;  // nnzb
     uint16_t* rank = nullptr;    // nelem*npe*npe
+    uint16_t* rank_adj = nullptr;  // the same rows in visit (adjacency) order: contiguous per node for the CSR reduction
     int max_cnt = 0;           // widest row in nodes
 };
 

@@ -38,6 +38,15 @@ __global__ void lower_bound_kernel(const K* __restrict__ keys, int64_t nkeys, K 
     ptr[n] = lo;
 }
 
+// rank rows reordered by visit (adjacency position): the reduction of node n then reads one contiguous run of uint16
+__global__ void reorder_rank_kernel(const uint16_t* __restrict__ rank, const int32_t* __restrict__ adj_idx, int64_t nvisit, int npe,
+                                    uint16_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nvisit * npe) return;
+    const int64_t k = i / npe;
+    out[i] = rank[(int64_t)adj_idx[k] * npe + (i - k * npe)];
+}
+
 __global__ void max_diff_kernel(const int64_t* __restrict__ ptr, int64_t n, int* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) atomicMax(out, (int)(ptr[i + 1] - ptr[i]));
@@ -158,6 +167,8 @@ int pattern_build(fl_handle* h) {
     }
     FL_CUDA_CHECK(cudaMalloc(&p.rank, sizeof(uint16_t) * total));
     rank_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->conn, h->nelem, npe, p.nbr_ptr, p.nbr_idx, p.rank);
+    FL_CUDA_CHECK(cudaMalloc(&p.rank_adj, sizeof(uint16_t) * (total > 0 ? total : 1)));
+    reorder_rank_kernel<<<(unsigned)((total + 255) / 256), 256>>>(p.rank, h->adj_idx, h->nelem * npe, npe, p.rank_adj);
     FL_CUDA_CHECK(cudaGetLastError());
     FL_CUDA_CHECK(cudaDeviceSynchronize());
     return FL_OK;
@@ -276,7 +287,7 @@ int launch_coo_indices(fl_handle* h, int nvar, int32_t* I, int32_t* J, cudaStrea
 template <int NV, int NPE>
 __global__ void __launch_bounds__(256)
 csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
-                  const uint16_t* __restrict__ rank, const double* __restrict__ ke, int64_t nnode, int npe_rt, int wmax,
+                  const uint16_t* __restrict__ rank_adj, const double* __restrict__ ke, int64_t nnode, int npe_rt, int wmax,
                   double* __restrict__ V) {
     extern __shared__ double rowbuf[];
     const int npe = NPE ? NPE : npe_rt;
@@ -286,64 +297,76 @@ csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     double* buf = rowbuf + (size_t)warp * NV * wmax;
+    // per-warp stage of the rank rows of up to 32 visits (behind the row buffers of all warps)
+    uint16_t* rks = reinterpret_cast<uint16_t*>(rowbuf + (size_t)wpb * NV * wmax) + (size_t)warp * 32 * npe;
     for (int64_t n = blockIdx.x * (int64_t)wpb + warp; n < nnode; n += (int64_t)gridDim.x * wpb) {
         const int w = (int)(nbr_ptr[n + 1] - nbr_ptr[n]) * NV;
         for (int t = lane; t < NV * w; t += 32) buf[t] = 0.0;
-        __syncwarp();
         const int64_t k0 = adj_ptr[n], k1 = adj_ptr[n + 1];
-        if (run <= MAXT * 32) {
-            // destination offsets depend only on (t, rank): i*w + rank[b]*NV + l
-            for (int64_t k = k0; k < k1; k += 2) {
-                const bool two = (k + 1 < k1);
-                const int64_t f0 = adj_idx[k], f1 = two ? adj_idx[k + 1] : f0;
-                const int64_t ea = f0 / npe, eb = f1 / npe;
-                const int aa = (int)(f0 - ea * npe), ab = (int)(f1 - eb * npe);
-                const double* ra = ke + ea * (int64_t)ndof * ndof + (int64_t)(aa * NV) * ndof;
-                const double* rb = ke + eb * (int64_t)ndof * ndof + (int64_t)(ab * NV) * ndof;
-                const uint16_t* qa = rank + f0 * npe;
-                const uint16_t* qb = rank + f1 * npe;
-                double va[MAXT], vb[MAXT];
-                int da[MAXT], db[MAXT];
+        for (int64_t kc = k0; kc < k1; kc += 32) {
+            // One dependent global round trip per 32 visits instead of two per pair of visits: every lane fetches the flat
+            // connectivity index of one visit, and the visits' rank rows (contiguous in adjacency order) are staged in shared
+            // memory.  ncu had 60 % of this kernel's stall samples on the integer ops consuming the per-visit rank loads.
+            const int nv = (int)min((int64_t)32, k1 - kc);
+            const int32_t fl = lane < nv ? adj_idx[kc + lane] : 0;
+            __syncwarp();
+            for (int t = lane; t < nv * npe; t += 32) rks[t] = rank_adj[kc * npe + t];
+            __syncwarp();
+            if (run <= MAXT * 32) {
+                // destination offsets depend only on (t, rank): i*w + rank[b]*NV + l
+                for (int v = 0; v < nv; v += 2) {
+                    const bool two = (v + 1 < nv);
+                    const int64_t f0 = __shfl_sync(0xffffffffu, fl, v), f1 = __shfl_sync(0xffffffffu, fl, two ? v + 1 : v);
+                    const int64_t ea = f0 / npe, eb = f1 / npe;
+                    const int aa = (int)(f0 - ea * npe), ab = (int)(f1 - eb * npe);
+                    const double* ra = ke + ea * (int64_t)ndof * ndof + (int64_t)(aa * NV) * ndof;
+                    const double* rb = ke + eb * (int64_t)ndof * ndof + (int64_t)(ab * NV) * ndof;
+                    const uint16_t* qa = rks + v * npe;
+                    const uint16_t* qb = rks + (two ? v + 1 : v) * npe;
+                    double va[MAXT], vb[MAXT];
+                    int da[MAXT], db[MAXT];
 #pragma unroll
-                for (int u = 0; u < MAXT; ++u) {
-                    const int t = lane + 32 * u;
-                    if (t < run) {
-                        const int i = t / ndof, c = t - i * ndof;
-                        const int b = c / NV, l = c - b * NV;
-                        va[u] = ra[t];
-                        da[u] = i * w + (int)qa[b] * NV + l;
-                        if (two) {
-                            vb[u] = rb[t];
-                            db[u] = i * w + (int)qb[b] * NV + l;
+                    for (int u = 0; u < MAXT; ++u) {
+                        const int t = lane + 32 * u;
+                        if (t < run) {
+                            const int i = t / ndof, c = t - i * ndof;
+                            const int b = c / NV, l = c - b * NV;
+                            va[u] = ra[t];
+                            da[u] = i * w + (int)qa[b] * NV + l;
+                            if (two) {
+                                vb[u] = rb[t];
+                                db[u] = i * w + (int)qb[b] * NV + l;
+                            }
                         }
                     }
-                }
-#pragma unroll
-                for (int u = 0; u < MAXT; ++u)
-                    if (lane + 32 * u < run) buf[da[u]] += va[u];
-                __syncwarp();
-                if (two) {
 #pragma unroll
                     for (int u = 0; u < MAXT; ++u)
-                        if (lane + 32 * u < run) buf[db[u]] += vb[u];
+                        if (lane + 32 * u < run) buf[da[u]] += va[u];
+                    __syncwarp();
+                    if (two) {
+#pragma unroll
+                        for (int u = 0; u < MAXT; ++u)
+                            if (lane + 32 * u < run) buf[db[u]] += vb[u];
+                        __syncwarp();
+                    }
+                }
+            } else {
+                for (int v = 0; v < nv; ++v) {
+                    const int64_t flat = __shfl_sync(0xffffffffu, fl, v);
+                    const int64_t e = flat / npe;
+                    const int a = (int)(flat - e * npe);
+                    const uint16_t* rk = rks + v * npe;
+                    const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof;
+                    for (int t = lane; t < run; t += 32) {
+                        const int i = t / ndof, c = t - i * ndof;
+                        const int b = c / NV, l = c - b * NV;
+                        buf[i * w + (int)rk[b] * NV + l] += krow[t];
+                    }
                     __syncwarp();
                 }
             }
-        } else {
-            for (int64_t k = k0; k < k1; ++k) {
-                const int64_t flat = adj_idx[k];
-                const int64_t e = flat / npe;
-                const int a = (int)(flat - e * npe);
-                const uint16_t* rk = rank + flat * npe;
-                const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof;
-                for (int t = lane; t < run; t += 32) {
-                    const int i = t / ndof, c = t - i * ndof;
-                    const int b = c / NV, l = c - b * NV;
-                    buf[i * w + (int)rk[b] * NV + l] += krow[t];
-                }
-                __syncwarp();
-            }
         }
+        __syncwarp();
         const int64_t base = nbr_ptr[n] * NV * NV;
         for (int t = lane; t < NV * w; t += 32) V[base + t] = buf[t];
         __syncwarp();
@@ -418,7 +441,7 @@ template <int NV, int NPE>
 static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     const Pattern& p = h->pat;
     const int wmax = p.max_cnt * NV;
-    const size_t per_warp = sizeof(double) * NV * wmax;
+    const size_t per_warp = sizeof(double) * NV * wmax + ((sizeof(uint16_t) * 32 * h->npe + 7) & ~(size_t)7);   // row buffer + rank stage
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 48 * 1024) wpb >>= 1;
     const size_t smem = per_warp * wpb;
@@ -434,7 +457,7 @@ static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaSt
     int64_t blocks = (h->nnode + wpb - 1) / wpb;
     const int64_t cap = (int64_t)h->sm_count * occ * 4;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, wmax, V);
+    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->npe, wmax, V);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }
