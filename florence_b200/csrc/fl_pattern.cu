@@ -374,57 +374,110 @@ csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict
 }
 
 // Wide rows (high-order elements: nvar*ndof > 128 doubles per visit): one block per node, the threads split each visit's run.
-template <int NV>
+template <int NV, int NPE_T>
 __global__ void __launch_bounds__(256)
 csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
-                       const uint16_t* __restrict__ rank, const double* __restrict__ ke, int64_t nnode, int npe, int plane_major,
-                       double* __restrict__ V) {
+                       const uint16_t* __restrict__ rank_adj, const double* __restrict__ ke, int64_t nnode, int npe_rt, int plane_major,
+                       int wmax, int max_adj, double* __restrict__ V) {
     extern __shared__ double rowbuf[];
+    const int npe = NPE_T ? NPE_T : npe_rt;   // compile-time for hex27 / hex64: the index arithmetic below becomes shifts and constants
     const int ndof = npe * NV;
     const int run = NV * ndof;
+    // register tile: the next visit's values are loaded before the current visit is added
+    constexpr int MAXR = NPE_T ? (NV * NV * NPE_T + 255) / 256 : 4;
+    // behind the row buffer: flat connectivity index and rank row of every visit of the node (one global round trip per node
+    // instead of two dependent ones per visit)
+    int32_t* flats = reinterpret_cast<int32_t*>(rowbuf + (size_t)NV * wmax);
+    uint16_t* rks = reinterpret_cast<uint16_t*>(flats + ((max_adj + 1) & ~1));
     for (int64_t n = blockIdx.x; n < nnode; n += gridDim.x) {
         const int w = (int)(nbr_ptr[n + 1] - nbr_ptr[n]) * NV;
+        const int64_t k0 = adj_ptr[n];
+        const int nvis = (int)(adj_ptr[n + 1] - k0);
         __syncthreads();
         for (int t = threadIdx.x; t < NV * w; t += blockDim.x) rowbuf[t] = 0.0;
+        for (int t = threadIdx.x; t < nvis; t += blockDim.x) flats[t] = adj_idx[k0 + t];
+        for (int t = threadIdx.x; t < nvis * npe; t += blockDim.x) rks[t] = rank_adj[k0 * npe + t];
         __syncthreads();
-        const int64_t k1 = adj_ptr[n + 1];
-        for (int64_t k = adj_ptr[n]; k < k1; ++k) {
-            const int64_t flat = adj_idx[k];
+        // source offset (relative to ke) and destination slot of item t of visit v
+        auto src_of = [&](int v, int t) -> int64_t {
+            const int64_t flat = flats[v];
             const int64_t e = flat / npe;
             const int a = (int)(flat - e * npe);
-            const uint16_t* rk = rank + flat * npe;
-            const double* krow = ke + e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof;
             if (plane_major) {
                 // K_e scratch stored as dof-pair planes [(i,l)][a][b] (DMMA element kernels): npe-long contiguous runs
-                const double* kel = ke + e * (int64_t)ndof * ndof + (int64_t)a * npe;
-                for (int t = threadIdx.x; t < run; t += blockDim.x) {
-                    const int il = t / npe, b = t - il * npe;
-                    const int i = il / NV, l = il - i * NV;
-                    rowbuf[i * w + (int)rk[b] * NV + l] += kel[(int64_t)il * npe * npe + b];
-                }
-            } else {
-                for (int t = threadIdx.x; t < run; t += blockDim.x) {
-                    const int i = t / ndof, c = t - i * ndof;
-                    const int b = c / NV, l = c - b * NV;
-                    rowbuf[i * w + (int)rk[b] * NV + l] += krow[t];
-                }
+                const int il = t / npe, b = t - il * npe;
+                return e * (int64_t)ndof * ndof + ((int64_t)il * npe + a) * npe + b;
             }
-            __syncthreads();
+            return e * (int64_t)ndof * ndof + (int64_t)(a * NV) * ndof + t;
+        };
+        auto dst_of = [&](int v, int t) -> int {
+            const uint16_t* rk = rks + v * npe;
+            if (plane_major) {
+                // consecutive lanes hold consecutive column nodes b of one (i,l) plane: the row buffer is kept as component
+                // planes [(i,l)][rank] so that they land in distinct banks (rank*NV + l would be an NV*2-way conflict)
+                const int il = t / npe, b = t - il * npe;
+                return il * (w / NV) + (int)rk[b];
+            }
+            const int i = t / ndof, c = t - i * ndof;
+            const int b = c / NV, l = c - b * NV;
+            return i * w + (int)rk[b] * NV + l;
+        };
+        if (run <= MAXR * (int)blockDim.x) {
+            double nxt[MAXR];
+#pragma unroll
+            for (int u = 0; u < MAXR; ++u) {
+                const int t = threadIdx.x + u * blockDim.x;
+                nxt[u] = (nvis > 0 && t < run) ? ke[src_of(0, t)] : 0.0;
+            }
+            for (int v = 0; v < nvis; ++v) {
+                double cur[MAXR];
+#pragma unroll
+                for (int u = 0; u < MAXR; ++u) cur[u] = nxt[u];
+                if (v + 1 < nvis) {
+#pragma unroll
+                    for (int u = 0; u < MAXR; ++u) {
+                        const int t = threadIdx.x + u * blockDim.x;
+                        if (t < run) nxt[u] = ke[src_of(v + 1, t)];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < MAXR; ++u) {
+                    const int t = threadIdx.x + u * blockDim.x;
+                    if (t < run) rowbuf[dst_of(v, t)] += cur[u];
+                }
+                __syncthreads();
+            }
+        } else {
+            for (int v = 0; v < nvis; ++v) {
+                for (int t = threadIdx.x; t < run; t += blockDim.x) rowbuf[dst_of(v, t)] += ke[src_of(v, t)];
+                __syncthreads();
+            }
         }
         const int64_t base = nbr_ptr[n] * NV * NV;
-        for (int t = threadIdx.x; t < NV * w; t += blockDim.x) V[base + t] = rowbuf[t];
+        if (plane_major) {
+            const int cn = w / NV;
+            for (int t = threadIdx.x; t < NV * w; t += blockDim.x) {
+                const int i = t / w, c = t - i * w;
+                const int r = c / NV, l = c - r * NV;
+                V[base + t] = rowbuf[(i * NV + l) * cn + r];
+            }
+        } else {
+            for (int t = threadIdx.x; t < NV * w; t += blockDim.x) V[base + t] = rowbuf[t];
+        }
     }
 }
 
-template <int NV>
+template <int NV, int NPE_T>
 static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     const Pattern& p = h->pat;
-    const size_t smem = sizeof(double) * NV * (size_t)p.max_cnt * NV;
+    const int wmax = p.max_cnt * NV;
+    const size_t smem = sizeof(double) * NV * (size_t)wmax + sizeof(int32_t) * ((h->max_adj + 1) & ~1) +
+                        ((sizeof(uint16_t) * (size_t)h->max_adj * h->npe + 7) & ~(size_t)7);
     if (smem > (size_t)h->max_smem_optin) {
         set_error("CSR rows of %d entries do not fit shared memory", p.max_cnt * NV);
         return FL_ERR_UNSUPPORTED;
     }
-    auto kern = csr_gather_wide_kernel<NV>;
+    auto kern = csr_gather_wide_kernel<NV, NPE_T>;
     FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
@@ -432,7 +485,8 @@ static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cud
     int64_t blocks = h->nnode;
     const int64_t cap = (int64_t)h->sm_count * occ * 8;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank, ke, h->nnode, h->npe, h->ke_plane_major, V);
+    kern<<<(unsigned)blocks, 256, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->npe, h->ke_plane_major, wmax,
+                                              h->max_adj, V);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }
@@ -464,7 +518,11 @@ static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaSt
 
 template <int NV>
 static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
-    if (NV * NV * h->npe > 128) return launch_csr_gather_wide<NV>(h, ke, V, st);
+    if (NV * NV * h->npe > 128) {
+        if (h->npe == 64) return launch_csr_gather_wide<NV, 64>(h, ke, V, st);
+        if (h->npe == 27) return launch_csr_gather_wide<NV, 27>(h, ke, V, st);
+        return launch_csr_gather_wide<NV, 0>(h, ke, V, st);
+    }
     switch (h->npe) {
         case 4: return launch_csr_gather_T<NV, 4>(h, ke, V, st);
         case 8: return launch_csr_gather_T<NV, 8>(h, ke, V, st);
