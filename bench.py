@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=55, help="hexes per edge before the 6-tet split (55 -> 998250 tet10)")
-    ap.add_argument("--explicit-n", type=int, default=160, help="hexes per edge of the hex27 explicit line (per GPU)")
+    ap.add_argument("--explicit-n", type=int, default=200, help="hexes per edge of the hex27 explicit line (per GPU)")
     ap.add_argument("--explicit-steps", type=int, default=20)
     ap.add_argument("--no-explicit", action="store_true")
     ap.add_argument("--no-hiorder", action="store_true")
