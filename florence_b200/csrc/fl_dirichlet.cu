@@ -40,6 +40,18 @@ __global__ void new_id_kernel(const int32_t* __restrict__ is_in, const int32_t* 
     if (i < n_out) new_id[cols_out[i]] = -(int32_t)(i + 1);
 }
 
+// cmask[q] bit l = 1 <=> dof l of neighbour node nbr_idx[q] is free: the row kernels then read one contiguous byte run per node
+// instead of chasing nbr_idx -> new_id for every column
+__global__ void col_mask_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ new_id, int64_t nnzb, int nvar,
+                                uint8_t* __restrict__ cmask) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= nnzb) return;
+    const int64_t m = nbr_idx[q];
+    unsigned bits = 0;
+    for (int l = 0; l < nvar; ++l) bits |= (new_id[m * nvar + l] >= 0 ? 1u : 0u) << l;
+    cmask[q] = (uint8_t)bits;
+}
+
 // One warp per NODE of the full matrix: the nvar dof rows of a node share their column list, so the free/prescribed split of
 // the columns (new_id lookups, ballots, positions) is computed once and applied to every free row of the node.
 // MODE 0: count the free columns of each free row (cnt_b[rr]).  MODE 1: write the reduced column indices.
@@ -47,7 +59,7 @@ __global__ void new_id_kernel(const int32_t* __restrict__ is_in, const int32_t* 
 template <int MODE, int NV>
 __global__ void __launch_bounds__(256)
 dirichlet_rows_kernel(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ new_id,
-                      int64_t nnode, const int64_t* __restrict__ rowptr_b, int64_t* __restrict__ cnt_b,
+                      const uint8_t* __restrict__ cmask, int64_t nnode, const int64_t* __restrict__ rowptr_b, int64_t* __restrict__ cnt_b,
                       int32_t* __restrict__ indices_b, const double* __restrict__ V, double* __restrict__ V_b,
                       const double* __restrict__ applied, double load_factor, double* __restrict__ F, double* __restrict__ F_b) {
     const int lane = threadIdx.x & 31;
@@ -71,12 +83,15 @@ dirichlet_rows_kernel(const int64_t* __restrict__ nbr_ptr, const int32_t* __rest
         for (int t0 = 0; t0 < w; t0 += 32) {
             const int t = t0 + lane;
             const bool valid = t < w;
+            // free / prescribed from the per-pair mask (contiguous per node); the index itself is only needed for the reduced
+            // column numbers (MODE 1) and for prescribed columns with an applied value (MODE 2)
+            bool in = false;
             int id = -1;
             if (valid) {
-                const int r = t / NV;
-                id = new_id[(int64_t)nbr_idx[p0 + r] * NV + (t - r * NV)];
+                const int r = t / NV, l = t - r * NV;
+                in = (cmask[p0 + r] >> l) & 1;
+                if (MODE == 1 ? in : (MODE == 2 && !in && applied)) id = new_id[(int64_t)nbr_idx[p0 + r] * NV + l];
             }
-            const bool in = valid && id >= 0;
             const unsigned m = __ballot_sync(0xffffffffu, in);
             const int pos = running + __popc(m & ((1u << lane) - 1u));
             if (MODE == 1) {
@@ -97,7 +112,7 @@ dirichlet_rows_kernel(const int64_t* __restrict__ nbr_ptr, const int32_t* __rest
                 if (applied) {
                     bool use = false;
                     double a = 0.0;
-                    if (valid && id < 0) {
+                    if (valid && !in) {
                         a = applied[-id - 1];
                         use = !(fabs(a) <= 1e-8);          // ~np.isclose(a, 0.0)
                     }
@@ -145,7 +160,7 @@ static void launch_rows(const fl_handle* h, const Dirichlet& d, int64_t* cnt_b, 
     const int64_t cap = (int64_t)h->sm_count * 32;
     const unsigned grid = (unsigned)(need < cap ? (need > 0 ? need : 1) : cap);
 #define FL_ROWS(NV_)                                                                                                              \
-    dirichlet_rows_kernel<MODE, NV_><<<grid, 256, 0, st>>>(h->pat.nbr_ptr, h->pat.nbr_idx, d.new_id, h->nnode, d.rowptr_b, cnt_b, \
+    dirichlet_rows_kernel<MODE, NV_><<<grid, 256, 0, st>>>(h->pat.nbr_ptr, h->pat.nbr_idx, d.new_id, d.cmask, h->nnode, d.rowptr_b, cnt_b, \
                                                            indices_b, V, V_b, applied, load_factor, F, F_b)
     switch (d.nvar) {
         case 1: FL_ROWS(1); break;
@@ -163,7 +178,7 @@ __global__ void narrow_ptr_kernel(const int64_t* __restrict__ p, int64_t n, int3
 
 void dirichlet_free(fl_handle* h) {
     Dirichlet& d = h->dir;
-    cudaFree(d.new_id); cudaFree(d.cols_in); cudaFree(d.rowptr_b);
+    cudaFree(d.new_id); cudaFree(d.cols_in); cudaFree(d.rowptr_b); cudaFree(d.cmask);
     d = Dirichlet();
 }
 
@@ -208,6 +223,8 @@ int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_o
         FL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_in, scan, (int)N));
         const int64_t m = N > n_out ? N : n_out;
         new_id_kernel<<<(unsigned)((m + 255) / 256), 256>>>(is_in, scan, N, cols_out, n_out, d.new_id, d.cols_in);
+        FL_CUDA_CHECK(cudaMalloc(&d.cmask, h->pat.nnzb > 0 ? h->pat.nnzb : 1));
+        col_mask_kernel<<<(unsigned)((h->pat.nnzb + 255) / 256), 256>>>(h->pat.nbr_idx, d.new_id, h->pat.nnzb, nvar, d.cmask);
         launch_rows<0>(h, d, cnt_b, nullptr, nullptr, nullptr, nullptr, 0.0, nullptr, nullptr, 0);
     }
     FL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt_b, d.rowptr_b, (int)(d.n_in + 1)));

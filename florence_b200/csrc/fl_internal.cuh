@@ -40,6 +40,7 @@ struct Dirichlet {
     int32_t* new_id = nullptr;    // nvar*nnode: reduced index of a free dof, -(k+1) for the k-th prescribed dof
     int32_t* cols_in = nullptr;   // n_in
     int64_t* rowptr_b = nullptr;  // n_in+1
+    uint8_t* cmask = nullptr;     // per node pair of the pattern: bit l set <=> column dof l of the neighbour node is free
 };
 
 // Rigid-plane penalty contact (ExplicitPenaltyContactFormulation.py:145-184): nodes flagged in `surf` (the unique nodes of the
