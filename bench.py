@@ -283,6 +283,33 @@ def run_b200(args, rank, world, local_rank):
     d2h = Vh.nbytes + Th.nbytes
     assert np.array_equal(Vh, V.cpu().numpy()), "host path and device path disagree"
 
+    # ------------------------------------------------------------------ the same Newton-iteration assembly with K kept on the device
+    # (SURVEY.md 8f.1): host state in -> plug-in with device_out -> Dirichlet reduction on the device -> only the reduced residual F_b
+    # returns to the host; K_b stays in HBM for a device solver.  Bottom face clamped, top face displaced.
+    from florence_b200 import boundary
+    zc = pts_host[:, 2]
+    flags = np.full((pts_host.shape[0], 3), np.nan)
+    flags[np.isclose(zc, zc.min())] = 0.0
+    flags[np.isclose(zc, zc.max()), 2] = 0.01
+    bc = boundary.DeviceBoundaryCondition.from_flags(h, flags)
+    def newton_assembly():
+        Vd, Td = func(so, fs, fo, me, material, x_host, None, device_out=True)
+        Kb, Fb, _ = bc.ApplyDirichletGetReducedMatrices(Vd, Td, bc.applied_dirichlet, LoadFactor=1.0)
+        return Kb, assembly._to_host(Fb, "Fb")
+    for _ in range(2):
+        Kb, Fb_host = newton_assembly()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        Kb, Fb_host = newton_assembly()
+    torch.cuda.synchronize()
+    res_s = max_over_ranks(time.perf_counter() - t0)
+    launches += 4 * (e2e_steps + 2)
+    resident = {"value": nelem_owned * world * e2e_steps / res_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(Fb_host.nbytes), "nnz_reduced": int(bc.nnz_b), "n_free_dofs": int(bc.n_in),
+                "api": "plug-in (device_out=True) + boundary.DeviceBoundaryCondition.ApplyDirichletGetReducedMatrices; K_b stays on the device"}
+    del Kb
+
     # ------------------------------------------------------------------ roofline of the dominant kernel
     hbm_peak, peak_src = measured_peaks()
     nnode_per_elem = nnode / float(nelem_local)
@@ -340,6 +367,7 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "florence_b200.assembly._LowLevelAssemblyDF__LinearElastic_ (host numpy in, host numpy out)"},
+            "e2e_device_resident": resident,
             "roofline": roof, "roofline_fp64": roof64}
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N=1 only)
