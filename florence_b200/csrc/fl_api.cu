@@ -348,9 +348,14 @@ int fl_assemble_laplacian(fl_handle* h, const double* e_tensor_host, int is_hess
         if (rc) return rc;
         ke = h->ke;
     }
+    mark(h, 0, st);
     rc = launch_laplacian_elements(h, h->te, is_hessian_symmetric ? 1 : 0, ke, st);
     if (rc) return rc;
-    return scatter_stiffness(h, 1, mode, ke, I, J, V, st);
+    mark(h, 1, st);
+    rc = scatter_stiffness(h, 1, mode, ke, I, J, V, st);
+    mark(h, 2, st);
+    mark(h, 3, st);
+    return rc;
 }
 
 int fl_assemble_mass(fl_handle* h, double rho, int nvar, int mass_type, int mode, double* mass, int32_t* I, int32_t* J, double* V,
