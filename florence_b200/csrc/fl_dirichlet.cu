@@ -182,6 +182,15 @@ void dirichlet_free(fl_handle* h) {
     d = Dirichlet();
 }
 
+namespace {
+// temporary device allocation released on every exit path
+struct DevTmp {
+    void* p = nullptr;
+    ~DevTmp() { cudaFree(p); }
+    template <typename T> T* as() { return static_cast<T*>(p); }
+};
+}  // namespace
+
 int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_out) {
     if (!h->pat.nbr_ptr) { set_error("fl_dirichlet_build requires fl_pattern_build first"); return FL_ERR_STATE; }
     dirichlet_free(h);
@@ -189,21 +198,19 @@ int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_o
     const int64_t N = h->nnode * nvar;
     if (N >= ((int64_t)1 << 31)) { set_error("dof count exceeds int32 indexing"); return FL_ERR_INVALID; }
     if (n_out < 0 || n_out > N) { set_error("bad number of prescribed dofs"); return FL_ERR_INVALID; }
-    int32_t *is_in = nullptr, *scan = nullptr, *bad = nullptr;
-    int64_t* cnt_b = nullptr;
-    void* tmp = nullptr;
+    DevTmp is_in_b, scan_b, bad_b, cnt_b_b, tmp_b;
     size_t tmp_bytes = 0, tmp2 = 0;
     const unsigned gN = (unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1);
-    FL_CUDA_CHECK(cudaMalloc(&is_in, sizeof(int32_t) * (N + 1)));
-    FL_CUDA_CHECK(cudaMalloc(&scan, sizeof(int32_t) * (N + 1)));
-    FL_CUDA_CHECK(cudaMalloc(&bad, sizeof(int32_t)));
+    FL_CUDA_CHECK(cudaMalloc(&is_in_b.p, sizeof(int32_t) * (N + 1)));
+    FL_CUDA_CHECK(cudaMalloc(&scan_b.p, sizeof(int32_t) * (N + 1)));
+    FL_CUDA_CHECK(cudaMalloc(&bad_b.p, sizeof(int32_t)));
+    int32_t *is_in = is_in_b.as<int32_t>(), *scan = scan_b.as<int32_t>(), *bad = bad_b.as<int32_t>();
     FL_CUDA_CHECK(cudaMemset(bad, 0, sizeof(int32_t)));
     fill_i32_kernel<<<gN, 256>>>(is_in, N, 1);
     if (n_out) mark_out_kernel<<<(unsigned)((n_out + 255) / 256), 256>>>(cols_out, n_out, N, is_in, bad);
     int32_t bad_h = 0;
     FL_CUDA_CHECK(cudaMemcpy(&bad_h, bad, sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (bad_h) {
-        cudaFree(is_in); cudaFree(scan); cudaFree(bad);
         set_error("columns_out must be strictly ascending and within [0, nvar*nnode)");
         return FL_ERR_INVALID;
     }
@@ -213,12 +220,14 @@ int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_o
     FL_CUDA_CHECK(cudaMalloc(&d.new_id, sizeof(int32_t) * (N > 0 ? N : 1)));
     FL_CUDA_CHECK(cudaMalloc(&d.cols_in, sizeof(int32_t) * (d.n_in > 0 ? d.n_in : 1)));
     FL_CUDA_CHECK(cudaMalloc(&d.rowptr_b, sizeof(int64_t) * (d.n_in + 1)));
-    FL_CUDA_CHECK(cudaMalloc(&cnt_b, sizeof(int64_t) * (d.n_in + 1)));
+    FL_CUDA_CHECK(cudaMalloc(&cnt_b_b.p, sizeof(int64_t) * (d.n_in + 1)));
+    int64_t* cnt_b = cnt_b_b.as<int64_t>();
     FL_CUDA_CHECK(cudaMemset(cnt_b, 0, sizeof(int64_t) * (d.n_in + 1)));
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, is_in, scan, (int)N);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp2, cnt_b, d.rowptr_b, (int)(d.n_in + 1));
     if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
-    FL_CUDA_CHECK(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+    FL_CUDA_CHECK(cudaMalloc(&tmp_b.p, tmp_bytes > 0 ? tmp_bytes : 1));
+    void* tmp = tmp_b.p;
     if (N) {
         FL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_in, scan, (int)N));
         const int64_t m = N > n_out ? N : n_out;
@@ -230,7 +239,6 @@ int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_o
     FL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt_b, d.rowptr_b, (int)(d.n_in + 1)));
     FL_CUDA_CHECK(cudaMemcpy(&d.nnz_b, d.rowptr_b + d.n_in, sizeof(int64_t), cudaMemcpyDeviceToHost));
     FL_CUDA_CHECK(cudaGetLastError());
-    cudaFree(is_in); cudaFree(scan); cudaFree(bad); cudaFree(cnt_b); cudaFree(tmp);
     if (d.nnz_b >= ((int64_t)1 << 31)) { set_error("reduced nnz exceeds int32 indexing"); return FL_ERR_INVALID; }
     return FL_OK;
 }
