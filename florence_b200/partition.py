@@ -33,8 +33,12 @@ def element_blocks(nelem, world):
 
 
 def partition_mesh(points, elements, rank, world):
-    """Generic partitioner (host logic, any mesh): block of elements -> localised mesh + interface lists.
-    points (nnode x d) and elements (nelem x npe) are the GLOBAL arrays (numpy or CPU tensors)."""
+    """Generic partitioner (any mesh): block of elements -> localised mesh + interface lists.
+    points (nnode x d) and elements (nelem x npe) are the GLOBAL arrays.  numpy / CPU tensors take the host path; CUDA tensors are
+    localised on the device (torch.unique / searchsorted / isin), which is what makes Mesh.Partition's GetLocalisedMesh
+    (Mesh.py:7406-7409) usable at 10^7-10^8 elements."""
+    if isinstance(elements, torch.Tensor) and elements.is_cuda:
+        return _partition_mesh_device(points, elements, rank, world)
     pts = np.asarray(points)
     els = np.asarray(elements).astype(np.int64)
     blocks = element_blocks(els.shape[0], world)
@@ -49,6 +53,26 @@ def partition_mesh(points, elements, rank, world):
         if shared.size:
             neighbours[r] = torch.as_tensor(np.searchsorted(mine, shared).astype(np.int32))
     return Partition(rank, world, torch.as_tensor(pts[mine]), torch.as_tensor(local), torch.as_tensor(mine), neighbours)
+
+
+def _partition_mesh_device(points, elements, rank, world):
+    """partition_mesh on the device the mesh lives on: same result, tensors stay on that device."""
+    els = elements.long()
+    pts = points if isinstance(points, torch.Tensor) else torch.as_tensor(np.asarray(points))
+    pts = pts.to(els.device)
+    blocks = element_blocks(els.shape[0], world)
+    b0, b1 = blocks[rank]
+    mine = torch.unique(els[b0:b1])                                   # sorted
+    local = torch.searchsorted(mine, els[b0:b1].reshape(-1)).reshape(b1 - b0, -1)
+    neighbours = {}
+    for r in range(world):
+        if r == rank:
+            continue
+        other = torch.unique(els[blocks[r][0]:blocks[r][1]])
+        shared = mine[torch.isin(mine, other, assume_unique=True)]
+        if shared.numel():
+            neighbours[r] = torch.searchsorted(mine, shared).to(torch.int32)
+    return Partition(rank, world, pts[mine], local, mine, neighbours)
 
 
 def slab_partition_hex(nx, ny, nz_per_rank, p, rank, world, lengths_per_rank=(1.0, 1.0, 1.0), device="cpu"):

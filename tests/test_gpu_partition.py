@@ -76,3 +76,19 @@ def test_explicit_partial_forces_sum_to_the_global_force(p, n, world):
         hl.close()
     assert np.abs(Tsum - T).max() <= 1e-12 * np.abs(T).max()
     assert np.abs(Msum - M).max() <= 1e-13 * np.abs(M).max()
+
+
+@pytest.mark.parametrize("kind,p,n,world", [("hex", 2, 4, 3), ("tet", 2, 3, 4)])
+def test_device_localisation_equals_host_localisation(kind, p, n, world):
+    from florence_b200 import mesh as flmesh, partition
+    pts, els = (flmesh.box_tet_mesh if kind == "tet" else flmesh.box_hex_mesh)(n, n, n, p=p)
+    dev = torch.device("cuda:0")
+    for rank in range(world):
+        ph = partition.partition_mesh(pts.numpy(), els.numpy(), rank, world)
+        pd = partition.partition_mesh(pts.to(dev), els.to(dev), rank, world)
+        assert pd.points.is_cuda and pd.elements.is_cuda
+        assert torch.equal(pd.points.cpu(), ph.points) and torch.equal(pd.elements.cpu(), ph.elements.long())
+        assert torch.equal(pd.node_map.cpu(), ph.node_map.long())
+        assert sorted(pd.neighbours) == sorted(ph.neighbours)
+        for r in ph.neighbours:
+            assert torch.equal(pd.neighbours[r].cpu(), ph.neighbours[r])
