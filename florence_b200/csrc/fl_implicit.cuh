@@ -553,7 +553,7 @@ int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, co
         // p = 3 hexahedra: dense parent-space contraction on the fp64 tensor cores (fl_implicit_mma.cuh); hex27 only when
         // forced (option value 2): its 27 -> 32 tile padding makes the generic kernel the faster one
         if (h->use_mma_implicit == 2 && h->npe == 27 && h->ng == 27) return launch_impl_mma<MAT, 27, 27, 21>(h, Eulerx, Eulerp, prm, update, ke, te, st);
-        if (h->use_mma_implicit && h->npe == 64 && h->ng == 64) return launch_impl_mma<MAT, 64, 64, 12>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+        if (h->use_mma_implicit && h->npe == 64 && h->ng == 64) return launch_impl_mma<MAT, 64, 64, FL_IMMA_KC64>(h, Eulerx, Eulerp, prm, update, ke, te, st);
     }
     if constexpr (D == 3 && MAT == MAT_LINEAR_ELASTIC) {
         // tet10 / hex8 (8 Gauss points): warp-autonomous kernel, no block barriers, no staging tile (fl_implicit_warp.cuh)

@@ -18,7 +18,10 @@
 
 namespace fl {
 
-constexpr int IMMA_THREADS = 256;  // warps 0-3 issue the DMMAs, warps 4-7 produce the next W chunk (double buffer)
+#ifndef FL_IMMA_THREADS
+#define FL_IMMA_THREADS 256
+#endif
+constexpr int IMMA_THREADS = FL_IMMA_THREADS;  // warps 0-3 issue the DMMAs, the remaining warps produce the next W chunk (double buffer)
 
 template <int NPE, int NG, int NV, int KC>
 struct imma_shape {
@@ -39,8 +42,18 @@ __device__ __forceinline__ int voigt_index(int i, int k) {
     return s + 2;         // -> 3, 4, 5
 }
 
+// Two blocks per SM: while one block evaluates the per-element prologue (kinematics, Hessian, Chat: 64 of its 256 threads), the
+// other one keeps the tensor pipe busy.  That needs K chunks of 6 k-steps (107 KB of shared memory per block) and a 128-register
+// cap -- the prologue spills ~1.5 KB per thread to local memory, still a net win: 11.7 -> 10.9 ms on 13 824 hex64 elements
+// (1 block/SM: KC = 12 11.7 ms, KC = 6 12.5 ms; 192 threads x 2 blocks: 14.6 ms, the two producer warps cannot keep up).
+#ifndef FL_IMMA_MINB
+#define FL_IMMA_MINB 2
+#endif
+#ifndef FL_IMMA_KC64
+#define FL_IMMA_KC64 6
+#endif
 template <int MAT, int NPE, int NG, int KC>
-__global__ void __launch_bounds__(IMMA_THREADS, 1)
+__global__ void __launch_bounds__(IMMA_THREADS, FL_IMMA_MINB)
 implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                              const double* __restrict__ phi, const double* __restrict__ jm, const double* __restrict__ jmT,
                              const double* __restrict__ gw, int64_t nelem, int ldg, int update, MatParams prm,
@@ -230,7 +243,7 @@ implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
         for (int s = 0; s < NS; ++s) {
             const int ij = s / S::NCH, ch = s - ij * S::NCH;
             if (warp >= 4) {
-                if (s + 1 < NS) produce(s + 1, threadIdx.x - 128, 128);
+                if (s + 1 < NS) produce(s + 1, threadIdx.x - 128, IMMA_THREADS - 128);
             } else {
                 if (ch == 0) {
 #pragma unroll
