@@ -134,7 +134,7 @@ implicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __r
 #pragma unroll
             for (int i = 0; i < NV; ++i)
 #pragma unroll
-                for (int j = 0; j < NV; ++j) {
+                for (int j = i; j < NV; ++j) {   // only the dof pairs i <= j are contracted below (K^{ji} is the mirror image)
                     // tmp[k][q] = sum_l (C[i,k,j,l] + geo) iJx[l][q]
                     double tmp[3][3];
 #pragma unroll
