@@ -481,7 +481,7 @@ def run_b200(args, rank, world, local_rank):
                            "config": {"workload": "hex64 (p=3) IsotropicElectroMechanics_108 Newton-step K(CSR)+T, %d^3 elements per GPU" % n4,
                                       "ndof_per_element": 256, "nnz_per_gpu": nnz4},
                            "roofline": {"bound": "tensor", "achieved": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
-                                        "frac": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12 / dmma, "kernel": "implicit_elements_mma_kernel<EM_108,64,64,12>",
+                                        "frac": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12 / dmma, "kernel": "implicit_elements_mma_kernel<EM_108,64,64,6>",
                                         "kernel_ms": t4[0], "csr_gather_wide_ms": t4[1],
                                         "peak_source": "measured in this run (fl_measure_fp64_peak, mma.sync.m8n8k4.f64 loop)",
                                         "flops_per_element_executed_on_tensor_cores": fl_exec}}
