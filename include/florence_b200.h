@@ -169,7 +169,7 @@ int fl_explicit_update(fl_handle *h, double dt, double fext_scale, const double 
 
 /* Tuning switches (for tests and A/B timing): option 0 = use the tensor-core (DMMA) explicit kernels for
  * hex8/hex27 (default 1); option 1 = use the DMMA implicit kernels for hex27/hex64 (default 1); option 2 = use the
- * warp-autonomous LinearElastic kernel for tet10/hex8 (default 1). */
+ * warp-autonomous LinearElastic kernel: 1 = tet10 (default), 2 = tet10 and hex8, 0 = off. */
 int fl_set_option(fl_handle *h, int option, int value);
 
 /* Per-kernel device timing of the most recent fl_assemble_* call (CUDA events recorded on the call's stream):
