@@ -56,17 +56,22 @@ def _material_struct(material, name=None):
 _handle_cache = {}
 
 
+_FP_SAMPLES = 1 << 16
+
+
 def _array_key(a):
-    """Identity + cheap content fingerprint of a mesh/table array: a mesh that is modified in place (same buffer) must not
-    hit a stale device copy."""
+    """Identity + content fingerprint of a mesh/table array: a mesh that is modified in place (same buffer) must not hit a stale
+    device copy.  The fingerprint sums 65 536 strided samples (hashing 100 MB of connectivity in full would cost as much as the
+    assembly it guards); code that edits a few entries of mesh.points / mesh.elements in place between assemblies calls
+    invalidate_handles(mesh) -- the reference has no such cache because it re-reads the host arrays on every call."""
     if isinstance(a, torch.Tensor):
         flat = a.reshape(-1)
-        step = max(1, flat.numel() // 4096)
+        step = max(1, flat.numel() // _FP_SAMPLES)
         fp = float(flat[::step].double().sum().item()) if flat.numel() else 0.0
         return ("t", a.data_ptr(), tuple(a.shape), fp)
     a = np.asarray(a)
     flat = a.reshape(-1)
-    step = max(1, flat.shape[0] // 4096)
+    step = max(1, flat.shape[0] // _FP_SAMPLES)
     fp = float(flat[::step].astype(np.float64).sum()) if flat.shape[0] else 0.0
     return ("n", a.__array_interface__["data"][0], a.shape, fp)
 
@@ -74,16 +79,27 @@ def _array_key(a):
 def get_handle(mesh, function_space):
     """Device handle for (mesh, function_space); cached so repeated Newton / time steps do not re-upload the mesh.
     A handle owns its scratch buffers: it serves one assembly call at a time (the reference's natives are likewise called with
-    the GIL held)."""
+    the GIL held).  Eviction only drops the cache's reference: an integrator or boundary-condition object that still holds the
+    handle keeps it alive, and the device memory is released when the last holder lets go (AssemblyHandle.__del__)."""
     key = (_array_key(mesh.points), _array_key(mesh.elements), _array_key(function_space.Jm))
     ent = _handle_cache.get(key)
     if ent is not None:
         return ent
     if len(_handle_cache) >= 4:
-        _handle_cache.pop(next(iter(_handle_cache))).close()
+        _handle_cache.pop(next(iter(_handle_cache)))
     h = AssemblyHandle(mesh.points, mesh.elements, function_space.Jm, function_space.AllGauss, getattr(function_space, "Bases", None))
     _handle_cache[key] = h
     return h
+
+
+def invalidate_handles(mesh=None):
+    """Forget the cached device copy of `mesh` (all meshes when None) after an in-place edit of its arrays."""
+    if mesh is None:
+        _handle_cache.clear()
+        return
+    pk, ek = _array_key(mesh.points)[:3], _array_key(mesh.elements)[:3]
+    for key in [k for k in _handle_cache if k[0][:3] == pk or k[1][:3] == ek]:
+        _handle_cache.pop(key)
 
 
 def clear_handles():
@@ -92,15 +108,26 @@ def clear_handles():
     _handle_cache.clear()
 
 
+# Host results.  The reference returns freshly allocated numpy arrays from every call (np.zeros in the Cython wrappers,
+# _LowLevelAssemblyDF_.pyx:90-103), so callers may keep K from several assemblies alive at once (modified Newton, the K/M/D
+# combinations of the implicit dynamic integrators).  The default here is the same: every call returns arrays the caller owns.
+# The copy goes device -> pinned staging buffer -> fresh array; the staging buffers are reused and never handed out.
+# `reuse_host_buffers(True)` is the opt-in for loops that consume K before re-assembling: large results are then returned as
+# views of a 2-deep ring of pinned buffers (no 2.8 GB allocation + copy per call), valid until the next-but-one call.
 _pinned = {}
 _PINNED_RING = 2
+_reuse_host_buffers = False
+
+
+def reuse_host_buffers(enabled=True):
+    """Opt in to (or out of) zero-copy host results, see above.  Returns the previous setting."""
+    global _reuse_host_buffers
+    prev, _reuse_host_buffers = _reuse_host_buffers, bool(enabled)
+    return prev
 
 
 def _to_host(t, tag, defer=False):
-    """D2H into pinned host memory, returned as a numpy view.  The reference returns freshly allocated arrays; allocating (or
-    page-locking) gigabytes per call would cost more than the assembly itself, so large results rotate through a ring of
-    _PINNED_RING pinned buffers per (tag, size): an array returned by call i stays valid until call i + _PINNED_RING of the same
-    kind -- enough for Newton / time loops, which consume K before re-assembling.  Small results (< 64 MiB) are copied out."""
+    """D2H through pinned host memory; returns a numpy array (see the ownership note above)."""
     n = t.numel()
     key = (tag, t.dtype, n)
     ent = _pinned.get(key)
@@ -125,7 +152,9 @@ def _to_host(t, tag, defer=False):
 
 def _finish_host(buf):
     out = buf.numpy()
-    return out.copy() if out.nbytes < (64 << 20) else out
+    if _reuse_host_buffers and out.nbytes >= (64 << 20):
+        return out
+    return out.copy()
 
 
 def _to_host_many(items):

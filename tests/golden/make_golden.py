@@ -37,8 +37,9 @@ from Florence.FiniteElements.Assembly.ComputeSparsityPattern import ComputeSpars
 
 def make_mesh(etype, p, n):
     mesh = Mesh()
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
     if etype in ("hex", "tet"):
-        mesh.Parallelepiped(upper_right_front_point=(1.0, 0.8, 1.2), nx=n, ny=n, nz=n, element_type=etype)
+        mesh.Parallelepiped(upper_right_front_point=(1.0, 0.8, 1.2), nx=nx, ny=ny, nz=nz, element_type=etype)
     else:
         mesh.Rectangle(upper_right_point=(1.0, 0.8), nx=n, ny=n, element_type=etype)
     if etype == "tet":
@@ -150,6 +151,52 @@ def perturbed(mesh, rng, amp=0.02):
     return mesh.points + amp * h * rng.uniform(-1, 1, mesh.points.shape)
 
 
+def _asm_case(out, rng, etype, p, n, matname):
+    """One (mesh, material) case through the reference's AssembleForm; returns the fixture key."""
+    mesh = make_mesh(etype, p, n)
+    ndim = mesh.points.shape[1]
+    material, prm = material_of(matname, ndim)
+    material.has_low_level_dispatcher = False
+    electro = matname in ELEC
+    form = DisplacementPotentialFormulation(mesh) if electro else DisplacementFormulation(mesh)
+    nature = "linear" if matname == "LinearElastic" else "nonlinear"
+    fem_solver = FEMSolver(analysis_nature=nature, optimise=False, recompute_sparsity_pattern=True)
+    Eulerx = perturbed(mesh, rng)
+    Eulerp = None
+    if electro:
+        Eulerp = 9.0e3 * mesh.points[:, -1] / mesh.points[:, -1].max() + 10.0 * rng.uniform(-1, 1, mesh.points.shape[0])
+    K, T = AssembleForm(form, mesh, material, fem_solver, Eulerx=Eulerx.copy(), Eulerp=None if Eulerp is None else Eulerp.copy())
+    K = K.tocsr()
+    K.sum_duplicates()
+    K.sort_indices()
+    tag = ("n%d" % n) if np.isscalar(n) else ("n%dx%dx%d" % tuple(n))
+    key = "asm_%s%d_%s_%s" % (etype, p, tag, matname)
+    fs = form.function_spaces[0]
+    out[key + "_points"] = mesh.points
+    out[key + "_elements"] = mesh.elements.astype(np.int64)
+    out[key + "_Eulerx"] = Eulerx
+    if Eulerp is not None:
+        out[key + "_Eulerp"] = Eulerp
+    out[key + "_Jm"] = fs.Jm
+    out[key + "_AllGauss"] = fs.AllGauss
+    out[key + "_Bases"] = fs.Bases
+    out[key + "_K_data"] = K.data
+    out[key + "_K_indices"] = K.indices
+    out[key + "_K_indptr"] = K.indptr
+    out[key + "_T"] = T.ravel()
+    out[key + "_update"] = np.array(int(fem_solver.requires_geometry_update))
+    out[key + "_prm"] = np.array([prm.get(k, 0.0) for k in ("mu", "mu1", "mu2", "mu3", "mue", "lamb", "eps_1", "eps_2", "eps_3", "eps_e")])
+    # the reference's own native sparsity pattern + slot maps
+    idx, iptr, dl, dg = ComputeSparsityPattern(mesh, form.nvar)
+    out[key + "_sp_indices"] = idx
+    out[key + "_sp_indptr"] = iptr
+    if mesh.nelem * (form.nvar * mesh.elements.shape[1]) ** 2 < 400000:
+        out[key + "_sp_dl"] = dl
+        out[key + "_sp_dg"] = dg
+    print(key, K.shape, K.nnz, "update", fem_solver.requires_geometry_update)
+    return key
+
+
 def gen_assembly(out):
     """Global K, T from the reference's Python path on small meshes."""
     rng = np.random.default_rng(11)
@@ -162,50 +209,19 @@ def gen_assembly(out):
         ("tet", 2, 1, "IsotropicElectroMechanics_105"), ("quad", 2, 2, "IsotropicElectroMechanics_108"),
         ("tri", 2, 2, "IsotropicElectroMechanics_101"), ("hex", 3, 1, "IsotropicElectroMechanics_108"),
     ]
-    names = []
-    for etype, p, n, matname in cases:
-        mesh = make_mesh(etype, p, n)
-        ndim = mesh.points.shape[1]
-        material, prm = material_of(matname, ndim)
-        material.has_low_level_dispatcher = False
-        electro = matname in ELEC
-        form = DisplacementPotentialFormulation(mesh) if electro else DisplacementFormulation(mesh)
-        nature = "linear" if matname == "LinearElastic" else "nonlinear"
-        fem_solver = FEMSolver(analysis_nature=nature, optimise=False, recompute_sparsity_pattern=True)
-        Eulerx = perturbed(mesh, rng)
-        Eulerp = None
-        if electro:
-            Eulerp = 9.0e3 * mesh.points[:, -1] / mesh.points[:, -1].max() + 10.0 * rng.uniform(-1, 1, mesh.points.shape[0])
-        K, T = AssembleForm(form, mesh, material, fem_solver, Eulerx=Eulerx.copy(), Eulerp=None if Eulerp is None else Eulerp.copy())
-        K = K.tocsr()
-        K.sum_duplicates()
-        K.sort_indices()
-        key = "asm_%s%d_n%d_%s" % (etype, p, n, matname)
-        names.append(key)
-        fs = form.function_spaces[0]
-        out[key + "_points"] = mesh.points
-        out[key + "_elements"] = mesh.elements.astype(np.int64)
-        out[key + "_Eulerx"] = Eulerx
-        if Eulerp is not None:
-            out[key + "_Eulerp"] = Eulerp
-        out[key + "_Jm"] = fs.Jm
-        out[key + "_AllGauss"] = fs.AllGauss
-        out[key + "_Bases"] = fs.Bases
-        out[key + "_K_data"] = K.data
-        out[key + "_K_indices"] = K.indices
-        out[key + "_K_indptr"] = K.indptr
-        out[key + "_T"] = T.ravel()
-        out[key + "_update"] = np.array(int(fem_solver.requires_geometry_update))
-        out[key + "_prm"] = np.array([prm.get(k, 0.0) for k in ("mu", "mu1", "mu2", "mu3", "mue", "lamb", "eps_1", "eps_2", "eps_3", "eps_e")])
-        # the reference's own native sparsity pattern + slot maps
-        idx, iptr, dl, dg = ComputeSparsityPattern(mesh, form.nvar)
-        out[key + "_sp_indices"] = idx
-        out[key + "_sp_indptr"] = iptr
-        if mesh.nelem * (form.nvar * mesh.elements.shape[1]) ** 2 < 400000:
-            out[key + "_sp_dl"] = dl
-            out[key + "_sp_dg"] = dg
-        print(key, K.shape, K.nnz, "update", fem_solver.requires_geometry_update)
+    names = [_asm_case(out, rng, *case) for case in cases]
     out["asm_cases"] = np.array(names)
+
+
+def gen_assembly_hi(out):
+    """Multi-element high-order / electro-mechanical cases: every shared node of these meshes is visited
+    by 2-8 elements, so the plane-major K_e scratch + wide CSR reduction of the hex64 DMMA path and the electro hex27 path are
+    compared with the reference's own K on more than one visit per node.  Kept in a separate file so that golden_assembly.npz
+    (and the random stream its cases consumed) stays as committed."""
+    rng = np.random.default_rng(23)
+    cases = [("hex", 3, (2, 2, 1), "IsotropicElectroMechanics_108"), ("hex", 3, (2, 1, 2), "MooneyRivlin"),
+             ("hex", 2, (2, 2, 2), "IsotropicElectroMechanics_108"), ("hex", 2, (2, 2, 2), "IsotropicElectroMechanics_105")]
+    out["asm_cases"] = np.array([_asm_case(out, rng, *case) for case in cases])
 
 
 def gen_laplacian(out):
@@ -302,7 +318,8 @@ def gen_explicit(out):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "materials", "assembly", "laplacian", "explicit"]
-    gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, laplacian=gen_laplacian, explicit=gen_explicit)
+    gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, assembly_hi=gen_assembly_hi, laplacian=gen_laplacian,
+                explicit=gen_explicit)
     for w in which:
         out = {}
         gens[w](out)

@@ -166,3 +166,81 @@ def test_config5_hex8_mooney_rivlin_explicit_8M_elements():
     assert status == 0 and bool(torch.isfinite(Eulerx).all())
     assert float((Eulerx - pts.reshape(-1))[: 3 * (n + 1) * (n + 1)].abs().max()) == 0.0
     h.close()
+
+
+def test_config4_hex64_em108_24cubed():
+    """Config 4 at its benchmarked size: hex64 IsotropicElectroMechanics_108, 24^3 elements, K (CSR through the dof-pair-plane scratch
+    and the wide node-centric reduction, and COO through the element-major write path) + T.  Properties that do not need the oracle
+    at this size, plus 32 sampled element matrices against the oracle (_LowLevelAssemblyDPF_.h:45-198)."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    dev = torch.device("cuda:0")
+    n = 24
+    pts, els = flmesh.box_hex_mesh(n, n, n, p=3, device=dev)
+    assert els.shape == (13824, 64) and pts.shape == (389017, 3)
+    Bases, Jm, AG = flmesh.tables("hex", 3)
+    x = flmesh.perturbed_state(pts, 1.0 / (3 * n), 0.02, seed=11)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    phi = 9.0e3 * pts[:, 2] + 10.0 * (2.0 * torch.rand(pts.shape[0], dtype=torch.float64, device=dev, generator=g) - 1.0)
+    mu = 5.0e4
+    prm = dict(mu1=mu, mu2=mu, lamb=2.0 * mu * 0.4 / (1.0 - 0.8), eps_2=4.0 * 8.8541e-12)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases, device=dev)
+    mat = backend.make_material(8, 1200.0, **prm)
+    indices, indptr = h.sparsity_pattern(4)
+    nrow = 4 * pts.shape[0]
+    V, T = h.assemble_implicit(x, phi, mat, 1, True, mode="csr")
+    V2, T2 = h.assemble_implicit(x, phi, mat, 1, True, mode="csr")
+    assert torch.equal(V, V2) and torch.equal(T, T2)            # deterministic reduction
+    K = torch.sparse_csr_tensor(indptr.long(), indices.long(), V, size=(nrow, nrow))
+    mech = (torch.arange(nrow, device=dev) % 4) != 3
+    # the four blocks live on very different scales (SURVEY.md 8a): scale every check by the block it touches
+    rows_of = indptr.new_zeros(indices.numel(), dtype=torch.int64)
+    rows_of[indptr[1:-1].long()] = 1
+    rows_of = torch.cumsum(rows_of, 0)
+    rm, cm = mech[rows_of], mech[indices.long()]
+    s_uu = float(V[rm & cm].abs().max()); s_up = float(V[rm & ~cm].abs().max()); s_pp = float(V[~rm & ~cm].abs().max())
+    # null space: a rigid translation produces no force and no charge; a constant potential shift neither (E = -grad phi)
+    for c in range(3):
+        r = torch.zeros(nrow, dtype=torch.float64, device=dev)
+        r[c::4] = 1.0
+        y = K @ r
+        assert float(y[mech].abs().max()) <= 1e-9 * s_uu and float(y[~mech].abs().max()) <= 1e-9 * s_up
+    r = torch.zeros(nrow, dtype=torch.float64, device=dev)
+    r[3::4] = 1.0
+    y = K @ r
+    assert float(y[mech].abs().max()) <= 1e-9 * s_up and float(y[~mech].abs().max()) <= 1e-9 * s_pp
+    # symmetry, block by block: y^T K z == z^T K y with y, z supported on one field each
+    ym = torch.rand(nrow, dtype=torch.float64, device=dev, generator=g)
+    zm = torch.rand(nrow, dtype=torch.float64, device=dev, generator=g)
+    for ya, za in ((mech, mech), (mech, ~mech), (~mech, ~mech)):
+        yy, zz = ym * ya, zm * za
+        a, b = float(yy @ (K @ zz)), float(zz @ (K @ yy))
+        assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    # COO mode (element-major triplets, different write path and no reduction kernel) carries the same matrix and the same T
+    I, J, Vc, Tc = h.assemble_implicit(x, phi, mat, 1, True, mode="coo")
+    assert torch.equal(Tc, T)
+    for ya, za in ((mech, mech), (mech, ~mech), (~mech, mech), (~mech, ~mech)):
+        yy, zz = ym * ya, zm * za
+        rhs = float(yy @ (K @ zz))
+        lhs = 0.0
+        step = 1 << 27
+        for k0 in range(0, Vc.numel(), step):
+            sl = slice(k0, min(k0 + step, Vc.numel()))
+            lhs += float((yy[I[sl].long()] * Vc[sl] * zz[J[sl].long()]).sum())
+        assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+    # 32 sampled element matrices against the oracle, block-wise
+    rng = np.random.default_rng(0)
+    sample = np.sort(rng.choice(els.shape[0], 32, replace=False))
+    st = torch.as_tensor(sample, device=dev)
+    P, X, PH = pts.cpu().numpy(), x.cpu().numpy(), phi.cpu().numpy()
+    E = els[st].cpu().numpy()
+    Io, Jo, Vo, To = orc.assemble_implicit(P, E, X, PH, Jm, AG, 4, 9, 1, orc.params(**prm), 8, mode="coo")
+    Vs = Vc.view(-1, 256, 256)[st].cpu().numpy()
+    Vo = Vo.reshape(-1, 256, 256)
+    m = np.arange(256) % 4 != 3
+    for ra in (m, ~m):
+        for ca in (m, ~m):
+            A, B = Vs[:, ra][:, :, ca], Vo[:, ra][:, :, ca]
+            assert np.abs(A - B).max() <= 1e-10 * np.abs(B).max()
+    del I, J, Vc
+    h.close()

@@ -1,7 +1,10 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden fixtures.
 
 Tolerances (fp64, BASELINE.json north_star): stiffness entries |dK| <= 1e-10 * max|K| (per block for electro-mechanics, whose
-blocks live on scales 20 orders of magnitude apart), residual ||dT|| <= 1e-11 ||T||; sparsity pattern and slot maps bit-exact.
+blocks live on scales 20 orders of magnitude apart) AND per entry: relative 1e-10 on every entry above 1e-3 * max|K| of its
+block, relative 1e-9 on every entry above 1e-6 * max|K| (entries that small are sums of terms of size max|K| that cancel to
+six digits, so one rounding of a term is already 1e-10 of the entry; the CPU oracle itself sits at 8e-11 of the reference
+there); residual ||dT|| <= 1e-11 ||T||; sparsity pattern and slot maps bit-exact.
 """
 import os
 
@@ -17,12 +20,16 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def _cases():
-    d = np.load(os.path.join(GOLD, "golden_assembly.npz"))
-    return [str(s) for s in d["asm_cases"]]
+    out = []
+    for f in ("golden_assembly.npz", "golden_assembly_hi.npz"):
+        out += [str(s) for s in np.load(os.path.join(GOLD, f))["asm_cases"]]
+    return out
 
 
 def _load(key):
     g = np.load(os.path.join(GOLD, "golden_assembly.npz"))
+    if key + "_points" not in g.files:
+        g = np.load(os.path.join(GOLD, "golden_assembly_hi.npz"))
     names = ("points", "elements", "Eulerx", "Jm", "AllGauss", "Bases", "K_data", "K_indices", "K_indptr", "T", "update", "prm",
              "sp_indices", "sp_indptr")
     c = {n: g[key + "_" + n] for n in names}
@@ -39,16 +46,28 @@ def _material(backend, num, prm):
                                  eps_2=prm[7], eps_3=prm[8], eps_e=prm[9])
 
 
+def _entrywise(A, B, tol):
+    """max-norm bound + per-entry relative bounds (module docstring); A, B sparse with any pattern."""
+    D = np.abs((A - B).toarray())
+    R = np.abs(B.toarray())
+    mx = R.max()
+    assert D.max() <= tol * mx
+    if tol < 1e-9:
+        return          # a tighter-than-parity identity check (e.g. CSR == summed COO): the max-norm bound is the statement
+    big, mid = R > 1e-3 * mx, R > 1e-6 * mx
+    assert (D[big] <= tol * R[big]).all(), "per-entry relative error %.2e" % (D[big] / R[big]).max()
+    assert (D[mid] <= 10 * tol * R[mid]).all(), "per-entry relative error %.2e" % (D[mid] / R[mid]).max()
+
+
 def _blockwise_close(K, Kref, nvar, ndim, tol):
     n = K.shape[0]
     if nvar == ndim:
-        assert abs(K - Kref).max() <= tol * abs(Kref).max()
+        _entrywise(K, Kref, tol)
         return
     mech = np.arange(n) % nvar != ndim
     for ra in (mech, ~mech):
         for ca in (mech, ~mech):
-            A, B = K[ra][:, ca], Kref[ra][:, ca]
-            assert abs(A - B).max() <= tol * abs(B).max()
+            _entrywise(K[ra][:, ca], Kref[ra][:, ca], tol)
 
 
 def _vec_close(T, Tref, nvar, ndim, tol):
@@ -114,7 +133,12 @@ def test_assembly_against_oracle_and_golden(key):
     K1 = csr_matrix((V1.cpu().numpy(), c["sp_indices"], c["sp_indptr"]), shape=(n, n))
     K1o = csr_matrix((V1o, c["sp_indices"], c["sp_indptr"]), shape=(n, n))
     _blockwise_close(K1, K1o, nvar, ndim, 1e-10)
+    _blockwise_close(K1, Kref, nvar, ndim, 1e-10)
     _vec_close(T1.cpu().numpy(), T1o, nvar, ndim, 1e-11)
+    # the CSR kernels (for hex64: dof-pair-plane scratch + wide reduction) against the scipy sum of the COO triplets of the same
+    # state, which come from the element-major write path: only the summation order differs
+    Kd = K.copy(); Kd.sum_duplicates(); Kd.sort_indices()
+    _blockwise_close(K1, Kd, nvar, ndim, 1e-13)
 
     # --- explicit (matrix-free) internal force
     if update == 1:
@@ -310,4 +334,50 @@ def test_implicit_tensor_core_kernel_equals_generic_kernel(key):
     K0 = csr_matrix((out[0][0], (out[0][2], out[0][3])), shape=(n, n))
     _blockwise_close(K1, K0, nvar, ndim, 1e-10)
     _vec_close(out[1][1], out[0][1], nvar, ndim, 1e-11)
+    h.close()
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 2, 2)])
+@pytest.mark.parametrize("matname", ["IsotropicElectroMechanics_108", "MooneyRivlin"])
+def test_hex64_multi_element_against_oracle(matname, shape):
+    """Config 4's kernels on meshes where interior nodes are visited by up to 8 elements: the DMMA element
+    kernel with its dof-pair-plane scratch and csr_gather_wide_kernel<NV,64> against the oracle, CSR and COO, and CSR against the
+    scipy sum of the COO triplets."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    nx, ny, nz = shape
+    pts, els = flmesh.box_hex_mesh(nx, ny, nz, p=3, lengths=(1.0, 0.8, 1.2))
+    Bases, Jm, AG = flmesh.tables("hex", 3)
+    x = flmesh.perturbed_state(pts, 1.0 / (3 * nx), 0.03, seed=17)
+    electro = matname in ELEC
+    num = orc.MATERIAL_NUMBERS[matname]
+    nvar, form, H = (4, 1, 9) if electro else (3, 0, 6)
+    rng = np.random.default_rng(3)
+    phi = (9.0e3 * pts[:, 2].numpy() + 10.0 * rng.uniform(-1, 1, pts.shape[0])) if electro else None
+    prm = dict(mu1=2.4e5, mu2=1.6e5, lamb=2.0e6)
+    if electro:
+        prm["eps_2"] = 4.0 * 8.8541e-12
+    P, E, X = pts.numpy(), els.numpy(), x.numpy()
+    n = nvar * P.shape[0]
+    h = backend.AssemblyHandle(pts, els, Jm, AG, Bases)
+    mat = backend.make_material(num, 0.0, **prm)
+    pat = orc.sparsity_pattern(E, P.shape[0], nvar)
+    indices, indptr = h.sparsity_pattern(nvar)
+    assert np.array_equal(indices.cpu().numpy(), pat[0]) and np.array_equal(indptr.cpu().numpy(), pat[1])
+    Io, Jo, Vo, To = orc.assemble_implicit(P, E, X, phi, Jm, AG, nvar, H, 1, orc.params(**prm), num, mode="coo")
+    Ko = csr_matrix((Vo, (Io, Jo)), shape=(n, n)); Ko.sum_duplicates(); Ko.sort_indices()
+    for opt in (1, 0):          # default (DMMA for hex64) and the generic column-owner kernel
+        h.set_option(1, opt)
+        I, J, V, T = h.assemble_implicit(x, phi, mat, form, True, mode="coo")
+        assert np.array_equal(I.cpu().numpy(), Io) and np.array_equal(J.cpu().numpy(), Jo)
+        K = csr_matrix((V.cpu().numpy(), (Io, Jo)), shape=(n, n)); K.sum_duplicates(); K.sort_indices()
+        _blockwise_close(K, Ko, nvar, 3, 1e-10)
+        _vec_close(T.cpu().numpy(), To, nvar, 3, 1e-11)
+        V1, T1 = h.assemble_implicit(x, phi, mat, form, True, mode="csr")
+        V1b, _ = h.assemble_implicit(x, phi, mat, form, True, mode="csr")
+        assert torch.equal(V1, V1b)
+        K1 = csr_matrix((V1.cpu().numpy(), pat[0], pat[1]), shape=(n, n))
+        _blockwise_close(K1, Ko, nvar, 3, 1e-10)
+        _blockwise_close(K1, K, nvar, 3, 1e-13)
+        _vec_close(T1.cpu().numpy(), To, nvar, 3, 1e-11)
     h.close()

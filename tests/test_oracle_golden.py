@@ -80,13 +80,16 @@ def _case(g, key):
 
 def _asm_cases():
     import os
-    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_assembly.npz"))
-    return [str(s) for s in d["asm_cases"]]
+    out = []
+    for f in ("assembly", "assembly_hi"):
+        d = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_%s.npz" % f))
+        out += [(f, str(s)) for s in d["asm_cases"]]
+    return out
 
 
-@pytest.mark.parametrize("key", _asm_cases())
-def test_implicit_assembly_vs_reference_python_path(golden, key):
-    c = _case(golden.assembly, key)
+@pytest.mark.parametrize("fixture,key", _asm_cases())
+def test_implicit_assembly_vs_reference_python_path(golden, fixture, key):
+    c = _case(getattr(golden, fixture), key)
     matname = key.split("_", 3)[3]
     num = orc.MATERIAL_NUMBERS[matname]
     nnode, ndim = c["points"].shape
