@@ -393,14 +393,15 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_explicit:
         ne = args.explicit_n
         part = partition.slab_partition_hex(ne, ne, ne, 2, rank, world, device=dev)
+        if world > 1:
+            part.interface_first()      # interface elements first: their forces are exchanged while the interior ones are evaluated
         Bs, Jh, AGh = flmesh.tables("hex", 2)
         hh = backend.AssemblyHandle(part.points, part.elements, Jh, AGh, Bs, device=dev)
         mu, lamb, rho = 4.0e5, 2.0e6, 1100.0
         mat_n = backend.make_material(1, rho, mu=mu, lamb=lamb)
         ex = None
         if world > 1:
-            pack, unpack = partition.device_pack_functions(hh)
-            ex = partition.InterfaceExchange(part, 3, dev, pack, unpack)
+            ex = partition.InterfaceExchange(part, 3, dev, handle=hh)
         integ = time_integrator.ExplicitStructuralDynamicIntegrator(hh, mat_n, rho=rho, exchange=ex)
         hx = 1.0 / ne
         dt_x = 0.2 * hx / np.sqrt((lamb + 2 * mu) / rho)

@@ -17,7 +17,9 @@ FL_MODE_COO, FL_MODE_CSR = 0, 1
 EXPORTS = ["fl_last_error", "fl_version", "fl_create", "fl_destroy", "fl_assemble_explicit", "fl_pattern_build", "fl_pattern_export",
            "fl_pattern_export_data_indices", "fl_assemble_implicit", "fl_assemble_laplacian", "fl_assemble_mass", "fl_explicit_steps",
            "fl_pack_nodes", "fl_unpack_add_nodes", "fl_explicit_update", "fl_measure_fp64_peak", "fl_set_timing", "fl_get_timing", "fl_set_option",
-           "fl_dirichlet_build", "fl_dirichlet_export", "fl_dirichlet_apply", "fl_set_contact", "fl_assemble_contact"]
+           "fl_dirichlet_build", "fl_dirichlet_export", "fl_dirichlet_apply", "fl_set_contact", "fl_assemble_contact",
+           "fl_scatter_nodes", "fl_sum_ordered", "fl_explicit_forces", "fl_gather_pack_nodes", "fl_gather_nodes", "fl_explicit_check",
+           "fl_row_block_build", "fl_row_block_emit", "fl_sfc_order"]
 
 
 class MeshDesc(C.Structure):
@@ -33,8 +35,15 @@ class Material(C.Structure):
 
 
 class ExplicitCtrl(C.Structure):
-    _fields_ = [("dt", C.c_double), ("fext_scale0", C.c_double), ("fext_scale_step", C.c_double), ("increment", C.c_int64),
-                ("nsteps", C.c_int64)]
+    _fields_ = [("dt", C.c_double), ("fext_scale0", C.c_double), ("fext_scale_step", C.c_double), ("incd_scale0", C.c_double),
+                ("incd_scale_step", C.c_double), ("increment", C.c_int64), ("nsteps", C.c_int64)]
+
+
+class UpdateArgs(C.Structure):
+    _fields_ = [("dt", C.c_double), ("fext_scale", C.c_double), ("incd_scale", C.c_double), ("M", C.c_void_p), ("fext", C.c_void_p),
+                ("fixed_mask", C.c_void_p), ("inc_dirichlet", C.c_void_p), ("T", C.c_void_p), ("iface_slot", C.c_void_p),
+                ("T_iface", C.c_void_p), ("U0", C.c_void_p), ("U00", C.c_void_p), ("Eulerx", C.c_void_p), ("status_dev", C.c_void_p),
+                ("growth_keys_dev", C.c_void_p), ("use_element_forces", C.c_int32), ("write_T", C.c_int32)]
 
 
 class FlorenceB200Error(RuntimeError):
@@ -72,7 +81,16 @@ def load():
     lib.fl_explicit_steps.argtypes = [vp, C.POINTER(Material), C.POINTER(ExplicitCtrl), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.fl_pack_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.fl_unpack_add_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
-    lib.fl_explicit_update.argtypes = [vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fl_scatter_nodes.argtypes = [vp, vp, i64, i32, vp, vp]
+    lib.fl_sum_ordered.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.fl_explicit_update.argtypes = [vp, C.POINTER(UpdateArgs), vp]
+    lib.fl_explicit_check.argtypes = [vp, vp, i64, vp, vp]
+    lib.fl_explicit_forces.argtypes = [vp, vp, C.POINTER(Material), i64, i64, vp]
+    lib.fl_gather_pack_nodes.argtypes = [vp, i32, vp, i64, vp, vp]
+    lib.fl_gather_nodes.argtypes = [vp, i32, vp, vp]
+    lib.fl_row_block_build.argtypes = [vp, i32, vp, i64, vp, C.POINTER(i64), vp]
+    lib.fl_row_block_emit.argtypes = [vp, i32, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.fl_sfc_order.argtypes = [vp, vp, i64, i32, i32, i64, vp, vp]
     lib.fl_set_option.argtypes = [vp, i32, i32]
     lib.fl_set_timing.argtypes = [vp, i32]
     lib.fl_get_timing.argtypes = [vp, C.POINTER(C.c_float)]

@@ -126,9 +126,67 @@ def reuse_host_buffers(enabled=True):
     return prev
 
 
+_BIG = 64 << 20          # bytes; below this a result is simply copied out of its staging buffer
+_CHUNK = 32 << 20        # bytes per staging chunk of the pipelined fresh-array path
+_stage = {}
+_pool = None
+
+
+def _fresh_from_device(t):
+    """Large result -> freshly allocated numpy array the caller owns: the tensor crosses PCIe in chunks through two pinned
+    staging buffers while a few host threads copy the previous chunk into the (pageable) result, so the copy-out and most of
+    the first-touch page faults hide behind the transfer."""
+    global _pool
+    from concurrent.futures import ThreadPoolExecutor
+    flat = t.reshape(-1)
+    n, isz = flat.numel(), flat.element_size()
+    out = np.empty(n, dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    per = max(1, _CHUNK // isz)
+    key = (t.dtype, per)
+    if key not in _stage:
+        _stage[key] = [torch.empty(per, dtype=t.dtype, pin_memory=True) for _ in range(2)]
+    bufs = _stage[key]
+    if _pool is None:
+        _pool = ThreadPoolExecutor(4)
+    stream = torch.cuda.current_stream()
+    pending = [None, None]          # per staging buffer: futures of the host copies still reading it
+    events = [None, None]
+
+    def drain(k, lo, hi):
+        events[k].synchronize()
+        src = bufs[k].numpy()[:hi - lo]
+        parts = 4
+        step = (hi - lo + parts - 1) // parts
+        pending[k] = [_pool.submit(np.copyto, out[lo + q * step:min(lo + (q + 1) * step, hi)], src[q * step:min((q + 1) * step, hi - lo)])
+                      for q in range(parts) if q * step < hi - lo]
+
+    prev = None
+    for i, lo in enumerate(range(0, n, per)):
+        hi, k = min(lo + per, n), i & 1
+        if pending[k] is not None:
+            for f in pending[k]:
+                f.result()
+        bufs[k][:hi - lo].copy_(flat[lo:hi], non_blocking=True)
+        events[k] = torch.cuda.Event()
+        events[k].record(stream)
+        if prev is not None:
+            drain(*prev)
+        prev = (k, lo, hi)
+    if prev is not None:
+        drain(*prev)
+    for k in (0, 1):
+        if pending[k] is not None:
+            for f in pending[k]:
+                f.result()
+    return out
+
+
 def _to_host(t, tag, defer=False):
     """D2H through pinned host memory; returns a numpy array (see the ownership note above)."""
     n = t.numel()
+    if not _reuse_host_buffers and n * t.element_size() >= _BIG:
+        out = _fresh_from_device(t)
+        return (out, None) if defer else out
     key = (tag, t.dtype, n)
     ent = _pinned.get(key)
     if ent is None:
@@ -151,8 +209,10 @@ def _to_host(t, tag, defer=False):
 
 
 def _finish_host(buf):
+    if isinstance(buf, np.ndarray):
+        return buf
     out = buf.numpy()
-    if _reuse_host_buffers and out.nbytes >= (64 << 20):
+    if _reuse_host_buffers and out.nbytes >= _BIG:
         return out
     return out.copy()
 
@@ -165,7 +225,8 @@ def _to_host_many(items):
     out = [None] * len(items)
     for i in order:
         buf, ev = pend[i]
-        ev.synchronize()
+        if ev is not None:
+            ev.synchronize()
         out[i] = _finish_host(buf)
     return tuple(out)
 
@@ -359,6 +420,13 @@ def install(florence_module=None):
         setattr(target, name, globals()[name])
         if hasattr(asm, name):
             setattr(asm, name, globals()[name])
+    # the process-pool launchers and the partitioner they rely on (Assembly.py:79-82, :672-682; FEMSolver.py:1630-1656)
+    for name in ("ImplicitParallelLauncher", "ExplicitParallelLauncher"):
+        setattr(asm, name, globals()[name])
+    fs = sys.modules.get(florence_module.__name__ + ".Solver.FEMSolver")
+    if fs is not None and hasattr(fs, "FEMSolver"):
+        from . import parallel
+        fs.FEMSolver.PartitionMeshForParallelFEM = parallel.PartitionMeshForParallelFEM
     target.has_low_level_dispatcher = True
     return target
 
@@ -378,9 +446,24 @@ def LowLevelAssembly(fem_solver, function_space, formulation, mesh, material, Eu
     if getattr(fem_solver, "analysis_type", "static") != "static" and getattr(fem_solver, "is_mass_computed", True) is False:
         M = _mass_for(fem_solver, function_space, formulation, mesh, material)
         fem_solver.is_mass_computed = True
-    stiffness, T, F, _ = _LowLevelAssembly_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+    if getattr(fem_solver, "parallel", False):                           # Assembly.py:79-82
+        stiffness, T, F, _ = ImplicitParallelLauncher(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+    else:
+        stiffness, T, F, _ = _LowLevelAssembly_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
     fem_solver.assembly_time = time() - t_assembly
     return stiffness, T[:, None], F, M
+
+
+def ImplicitParallelLauncher(*args, **kwargs):
+    """Assembly.py:879-1050 (see parallel.py)."""
+    from . import parallel
+    return parallel.ImplicitParallelLauncher(*args, **kwargs)
+
+
+def ExplicitParallelLauncher(*args, **kwargs):
+    """Assembly.py:1126-1358 (see parallel.py)."""
+    from . import parallel
+    return parallel.ExplicitParallelLauncher(*args, **kwargs)
 
 
 def Assemble(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp):
@@ -410,7 +493,10 @@ def AssembleExplicit(fem_solver, function_space, formulation, mesh, material, Eu
     """Assembly.py:664-715: (T[:,None], F, M); the first call also builds the (lumped or consistent) mass."""
     if not getattr(material, "has_low_level_dispatcher", True):
         raise RuntimeError("Cannot dispatch to low level module, since material {} does not support it".format(type(material).__name__))
-    T, F, M = _LowLevelAssemblyExplicit_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
+    if getattr(fem_solver, "parallel", False):                           # Assembly.py:672-674, :681-682
+        T, F, M = ExplicitParallelLauncher(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp), [], []
+    else:
+        T, F, M = _LowLevelAssemblyExplicit_(fem_solver, function_space, formulation, mesh, material, Eulerx, Eulerp)
     if getattr(fem_solver, "is_mass_computed", True) is True:
         return T[:, None], F, M
     M = _mass_for(fem_solver, function_space, formulation, mesh, material)

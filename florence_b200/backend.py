@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ExplicitCtrl, Material, MeshDesc, check
+from ._lib import ExplicitCtrl, Material, MeshDesc, UpdateArgs, check
 
 # Florence/FiniteElements/Assembly/_Assembly_/_LowLevelAssemblyExplicit_DF_DPF_.pyx:72-109
 MATERIAL_NUMBERS = {
@@ -281,18 +281,78 @@ class AssemblyHandle(object):
 
     # ---------------------------------------------------------------------------------------------- explicit time loop
     def explicit_steps(self, material, dt, nsteps, increment, M, fext, fixed_mask, inc_dirichlet, U0, U00, Eulerx, T,
-                       fext_scale0=0.0, fext_scale_step=0.0):
-        ctrl = ExplicitCtrl(float(dt), float(fext_scale0), float(fext_scale_step), int(increment), int(nsteps))
-        status = C.c_int32(0)
+                       fext_scale0=0.0, fext_scale_step=0.0, incd_scale0=1.0, incd_scale_step=0.0, full_status=False):
+        """`nsteps` central-difference increments on the device.  Returns the status bits (0 = fine, bit 0 = NaN, bit 1 = the
+        reference's growth test fired); with full_status, (bits, increment of the first detection)."""
+        ctrl = ExplicitCtrl(float(dt), float(fext_scale0), float(fext_scale_step), float(incd_scale0), float(incd_scale_step),
+                            int(increment), int(nsteps))
+        status = (C.c_int32 * 2)(0, 0)
         with torch.cuda.device(self.device):
             check(self.lib.fl_explicit_steps(self._h, C.byref(material), C.byref(ctrl), _ptr(M), _ptr(fext), _ptr(fixed_mask),
-                                             _ptr(inc_dirichlet), _ptr(U0), _ptr(U00), _ptr(Eulerx), _ptr(T), C.byref(status), _stream()))
-        return int(status.value)
+                                             _ptr(inc_dirichlet), _ptr(U0), _ptr(U00), _ptr(Eulerx), _ptr(T), status, _stream()))
+        return (int(status[0]), int(status[1])) if full_status else int(status[0])
 
-    def explicit_update(self, dt, fext_scale, M, fext, fixed_mask, inc_dirichlet, T, U0, U00, Eulerx, nan_flag=None):
+    def explicit_update(self, dt, fext_scale, M, fext, fixed_mask, inc_dirichlet, T, U0, U00, Eulerx, status=None, growth_keys=None,
+                        incd_scale=1.0, use_element_forces=False, write_T=False, iface_slot=None, T_iface=None):
+        """One update (fl_explicit_update).  status: int32[2] device tensor; growth_keys: int64[2] device tensor."""
+        a = UpdateArgs(float(dt), float(fext_scale), float(incd_scale), M.data_ptr(), 0 if fext is None else fext.data_ptr(),
+                       0 if fixed_mask is None else fixed_mask.data_ptr(), 0 if inc_dirichlet is None else inc_dirichlet.data_ptr(),
+                       T.data_ptr(), 0 if iface_slot is None else iface_slot.data_ptr(), 0 if T_iface is None else T_iface.data_ptr(),
+                       U0.data_ptr(), U00.data_ptr(), Eulerx.data_ptr(), 0 if status is None else status.data_ptr(),
+                       0 if growth_keys is None else growth_keys.data_ptr(), 1 if use_element_forces else 0, 1 if write_T else 0)
         with torch.cuda.device(self.device):
-            check(self.lib.fl_explicit_update(self._h, float(dt), float(fext_scale), _ptr(M), _ptr(fext), _ptr(fixed_mask),
-                                              _ptr(inc_dirichlet), _ptr(T), _ptr(U0), _ptr(U00), _ptr(Eulerx), _ptr(nan_flag), _stream()))
+            check(self.lib.fl_explicit_update(self._h, C.byref(a), _stream()))
+
+    def explicit_check(self, growth_keys, increment, status):
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_explicit_check(self._h, _ptr(growth_keys), int(increment), _ptr(status), _stream()))
+
+    def explicit_forces(self, Eulerx, material, e0=0, e1=None):
+        """Per-element internal forces of elements [e0, e1) into the handle's scratch."""
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_explicit_forces(self._h, _ptr(Eulerx), C.byref(material), int(e0), int(self.nelem if e1 is None else e1), _stream()))
+
+    def gather_pack_nodes(self, nvar, node_ids, buf):
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_gather_pack_nodes(self._h, nvar, _ptr(node_ids), node_ids.numel(), _ptr(buf), _stream()))
+
+    def gather_nodes(self, nvar, T):
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_gather_nodes(self._h, nvar, _ptr(T), _stream()))
+
+    # ---------------------------------------------------------------------------------------------- owned CSR row block
+    def row_block(self, nvar, V, owned_nodes, node_map):
+        """(indptr_block int64 [n_owned*nvar+1], cols_global int64, vals): the CSR rows of `owned_nodes` (ascending local ids) of the
+        locally assembled V with GLOBAL column dof numbers, produced on the device (fl_row_block_build / fl_row_block_emit)."""
+        own = to_device(owned_nodes, torch.int32, self.device).reshape(-1)
+        nmap = to_device(node_map, torch.int64, self.device).reshape(-1)
+        key = ("rowblock", nvar, own.data_ptr(), own.numel())
+        cache = getattr(self, "_row_block_cache", None)
+        if cache is None or cache[0] != key:
+            indptr = torch.empty(own.numel() * nvar + 1, dtype=torch.int64, device=self.device)
+            nnz = C.c_int64(0)
+            with torch.cuda.device(self.device):
+                check(self.lib.fl_row_block_build(self._h, nvar, _ptr(own), own.numel(), _ptr(indptr), C.byref(nnz), _stream()))
+            self._row_block_cache = cache = (key, indptr, int(nnz.value), own)
+        _, indptr, nnz, own = cache
+        cols = torch.empty(nnz, dtype=torch.int64, device=self.device)
+        vals = torch.empty(nnz, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.fl_row_block_emit(self._h, nvar, _ptr(V), _ptr(own), own.numel(), _ptr(nmap), _ptr(indptr), _ptr(cols), _ptr(vals),
+                                             _stream()))
+        return indptr, cols, vals
+
+
+def sfc_order(points, elements):
+    """Permutation that sorts the elements along a Morton curve through their centroids (fl_sfc_order), device tensors in/out."""
+    lib = _lib.load()
+    dev = elements.device
+    pts = to_device(points, torch.float64, dev)
+    els = to_device(elements, torch.int64, dev)
+    perm = torch.empty(els.shape[0], dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.fl_sfc_order(_ptr(pts), _ptr(els), els.shape[0], els.shape[1], pts.shape[1], pts.shape[0], _ptr(perm), _stream()))
+    return perm
 
 
 def _set_timing(self, enabled=True):

@@ -127,8 +127,13 @@ int fl_create(const fl_mesh_desc* m, fl_handle** out) {
     FL_TRY(cudaMalloc(&h->jmT, sizeof(double) * h->ndim * h->npe * h->ng));
     FL_TRY(cudaMalloc(&h->bases, sizeof(double) * h->npe * h->ng));
     FL_TRY(cudaMalloc(&h->gw, sizeof(double) * h->ng));
-    FL_TRY(cudaMalloc(&h->flag, sizeof(int32_t)));
-    FL_TRY(cudaMemset(h->flag, 0, sizeof(int32_t)));
+    FL_TRY(cudaMalloc(&h->flag, 4 * sizeof(int32_t)));
+    FL_TRY(cudaMemset(h->flag, 0, 4 * sizeof(int32_t)));
+    FL_TRY(cudaMalloc(&h->growth, 2 * sizeof(int64_t)));
+    {
+        const int64_t lowest[2] = {INT64_MIN, INT64_MIN};
+        FL_TRY(cudaMemcpy(h->growth, lowest, sizeof(lowest), cudaMemcpyHostToDevice));
+    }
     FL_TRY(cudaMemcpy(h->points, m->points, sizeof(double) * h->nnode * h->ndim, cudaMemcpyDeviceToDevice));
     FL_TRY(cudaMemcpy(h->gw, m->AllGauss, sizeof(double) * h->ng, cudaMemcpyDeviceToDevice));
     if (m->bases) FL_TRY(cudaMemcpy(h->bases, m->bases, sizeof(double) * h->npe * h->ng, cudaMemcpyDeviceToDevice));
@@ -189,7 +194,7 @@ int fl_destroy(fl_handle* h) {
     cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank); cudaFree(h->pat.rank_adj);
     dirichlet_free(h);
     cudaFree(h->contact.surf);
-    cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag);
+    cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag); cudaFree(h->growth);
     delete h;
     return FL_OK;
 }
@@ -385,12 +390,40 @@ int fl_assemble_mass(fl_handle* h, double rho, int nvar, int mass_type, int mode
     return scatter_stiffness(h, nvar, mode, ke, I, J, V, st);
 }
 
-int fl_explicit_update(fl_handle* h, double dt, double fext_scale, const double* M, const double* fext, const uint8_t* fixed_mask,
-                       const double* inc_dirichlet, const double* T, double* U0, double* U00, double* Eulerx, int32_t* nan_flag_dev,
-                       void* stream) {
-    if (!h || !M || !T || !U0 || !U00 || !Eulerx) { set_error("null argument"); return FL_ERR_INVALID; }
-    return launch_explicit_update(h, 0, nullptr, dt, fext_scale, M, fext, fixed_mask, inc_dirichlet, const_cast<double*>(T), U0, U00, Eulerx,
-                                  nan_flag_dev ? nan_flag_dev : h->flag, (cudaStream_t)stream);
+int fl_explicit_update(fl_handle* h, const fl_update_args* a, void* stream) {
+    if (!h || !a || !a->M || !a->T || !a->U0 || !a->U00 || !a->Eulerx) { set_error("null argument"); return FL_ERR_INVALID; }
+    if (a->use_element_forces && !h->te) { set_error("fl_explicit_forces has not been called"); return FL_ERR_STATE; }
+    if ((a->iface_slot == nullptr) != (a->T_iface == nullptr)) { set_error("iface_slot and T_iface go together"); return FL_ERR_INVALID; }
+    return launch_explicit_update(h, a->use_element_forces ? (a->write_T ? 2 : 1) : 0, h->te, a->dt, a->fext_scale, a->incd_scale, a->M, a->fext,
+                                  a->fixed_mask, a->inc_dirichlet, a->T, a->iface_slot, a->T_iface, a->U0, a->U00, a->Eulerx,
+                                  a->status_dev ? a->status_dev : h->flag, a->growth_keys_dev, (cudaStream_t)stream);
+}
+
+int fl_explicit_check(fl_handle* h, int64_t* growth_keys_dev, int64_t increment, int32_t* status_dev, void* stream) {
+    if (!h || !growth_keys_dev || !status_dev) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_growth_check(growth_keys_dev, increment, status_dev, (cudaStream_t)stream);
+}
+
+int fl_explicit_forces(fl_handle* h, const double* Eulerx, const fl_material* mat, int64_t e0, int64_t e1, void* stream) {
+    if (!h || !Eulerx || !mat) { set_error("null argument"); return FL_ERR_INVALID; }
+    if (e0 < 0 || e1 > h->nelem || e0 > e1) { set_error("bad element range [%lld, %lld)", (long long)e0, (long long)e1); return FL_ERR_INVALID; }
+    int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * h->npe * h->ndim);
+    if (rc) return rc;
+    h->el0 = e0; h->el1 = e1;
+    rc = launch_explicit_elements(h, Eulerx, nullptr, mat, 0, h->te, (cudaStream_t)stream);
+    h->el0 = 0; h->el1 = -1;
+    return rc;
+}
+
+int fl_gather_pack_nodes(fl_handle* h, int nvar, const int32_t* node_ids, int64_t n, double* buf, void* stream) {
+    if (n == 0) return FL_OK;
+    if (!h || !node_ids || !buf || !h->te) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_gather_pack(h, nvar, h->te, node_ids, n, buf, (cudaStream_t)stream);
+}
+
+int fl_gather_nodes(fl_handle* h, int nvar, double* T, void* stream) {
+    if (!h || !T || !h->te) { set_error("null argument"); return FL_ERR_INVALID; }
+    return launch_gather_nodes(h, nvar, h->te, T, (cudaStream_t)stream);
 }
 
 int fl_explicit_steps(fl_handle* h, const fl_material* mat, const fl_explicit_ctrl* c, const double* M, const double* fext,
@@ -401,11 +434,15 @@ int fl_explicit_steps(fl_handle* h, const fl_material* mat, const fl_explicit_ct
     const int nvar = h->ndim;
     int rc = ensure_scratch(&h->te, &h->te_bytes, sizeof(double) * h->nelem * h->npe * nvar);
     if (rc) return rc;
-    FL_CUDA_CHECK(cudaMemsetAsync(h->flag, 0, sizeof(int32_t), st));
+    FL_CUDA_CHECK(cudaMemsetAsync(h->flag, 0, 2 * sizeof(int32_t), st));
     for (int64_t s = 0; s < c->nsteps; ++s) {
         const double fs = c->fext_scale0 + (double)(c->increment + s) * c->fext_scale_step;
+        const double ds = c->incd_scale0 + (double)(c->increment + s) * c->incd_scale_step;
         // first step consumes the caller's T; later steps reduce the per-element tractions and update in one kernel
-        rc = launch_explicit_update(h, s == 0 ? 0 : 1, h->te, c->dt, fs, M, fext, fixed_mask, inc_dirichlet, T, U0, U00, Eulerx, h->flag, st);
+        rc = launch_explicit_update(h, s == 0 ? 0 : 1, h->te, c->dt, fs, ds, M, fext, fixed_mask, inc_dirichlet, T, nullptr, nullptr, U0, U00,
+                                    Eulerx, h->flag, h->growth, st);
+        if (rc) return rc;
+        rc = launch_growth_check(h->growth, c->increment + s, h->flag, st);
         if (rc) return rc;
         rc = launch_explicit_elements(h, Eulerx, nullptr, mat, 0, h->te, st);
         if (rc) return rc;
@@ -419,7 +456,7 @@ int fl_explicit_steps(fl_handle* h, const fl_material* mat, const fl_explicit_ct
         }
     }
     if (status_host) {
-        FL_CUDA_CHECK(cudaMemcpyAsync(status_host, h->flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FL_CUDA_CHECK(cudaMemcpyAsync(status_host, h->flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         FL_CUDA_CHECK(cudaStreamSynchronize(st));
     }
     return FL_OK;
@@ -439,6 +476,40 @@ __global__ void unpack_add_nodes_kernel(double* __restrict__ T, const int32_t* _
     T[(int64_t)ids[k] * nvar + (i - k * nvar)] += buf[i];
 }
 
+// out[k] = sum_j all[idx[j]..idx[j]+nvar) for j in [ptr[k], ptr[k+1]), added in list order (the lists are sorted by owner rank)
+__global__ void sum_ordered_kernel(const double* __restrict__ all, const int64_t* __restrict__ ptr, const int64_t* __restrict__ idx, int64_t n,
+                                   int nvar, double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n * nvar) return;
+    const int64_t k = i / nvar;
+    const int c = (int)(i - k * nvar);
+    double acc = 0.0;
+    for (int64_t j = ptr[k]; j < ptr[k + 1]; ++j) acc = __dadd_rn(acc, all[idx[j] + c]);
+    out[i] = acc;
+}
+__global__ void scatter_nodes_kernel(double* __restrict__ T, const int32_t* __restrict__ ids, int64_t n, int nvar, const double* __restrict__ buf) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n * nvar) return;
+    const int64_t k = i / nvar;
+    T[(int64_t)ids[k] * nvar + (i - k * nvar)] = buf[i];
+}
+
+int fl_sum_ordered(const double* all, const int64_t* ptr, const int64_t* idx, int64_t n, int nvar, double* out, void* stream) {
+    if (n == 0) return FL_OK;
+    if (!all || !ptr || !idx || !out) { set_error("null argument"); return FL_ERR_INVALID; }
+    sum_ordered_kernel<<<(unsigned)((n * nvar + 255) / 256), 256, 0, (cudaStream_t)stream>>>(all, ptr, idx, n, nvar, out);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+int fl_scatter_nodes(double* T, const int32_t* node_ids, int64_t n, int nvar, const double* buf, void* stream) {
+    if (n == 0) return FL_OK;
+    if (!T || !node_ids || !buf) { set_error("null argument"); return FL_ERR_INVALID; }
+    scatter_nodes_kernel<<<(unsigned)((n * nvar + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, node_ids, n, nvar, buf);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
 int fl_pack_nodes(const double* T, const int32_t* node_ids, int64_t n, int nvar, double* buf, void* stream) {
     if (n == 0) return FL_OK;
     if (!T || !node_ids || !buf) { set_error("null argument"); return FL_ERR_INVALID; }
@@ -453,6 +524,30 @@ int fl_unpack_add_nodes(double* T, const int32_t* node_ids, int64_t n, int nvar,
     unpack_add_nodes_kernel<<<(unsigned)((n * nvar + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, node_ids, n, nvar, buf);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
+}
+
+int fl_row_block_build(fl_handle* h, int nvar, const int32_t* owned_nodes, int64_t n_owned, int64_t* indptr_block, int64_t* nnz_block_host,
+                       void* stream) {
+    if (!h || nvar < 1 || nvar > 4 || n_owned < 0 || (n_owned > 0 && !owned_nodes) || !indptr_block) { set_error("bad argument"); return FL_ERR_INVALID; }
+    return launch_row_block_build(h, nvar, owned_nodes, n_owned, indptr_block, nnz_block_host, (cudaStream_t)stream);
+}
+
+int fl_row_block_emit(fl_handle* h, int nvar, const double* V, const int32_t* owned_nodes, int64_t n_owned, const int64_t* node_map,
+                      const int64_t* indptr_block, int64_t* cols_global, double* vals, void* stream) {
+    if (!h || nvar < 1 || nvar > 4 || !V || !node_map || !indptr_block || !cols_global || !vals || (n_owned > 0 && !owned_nodes)) {
+        set_error("bad argument");
+        return FL_ERR_INVALID;
+    }
+    return launch_row_block_emit(h, nvar, V, owned_nodes, n_owned, node_map, indptr_block, cols_global, vals, (cudaStream_t)stream);
+}
+
+int fl_sfc_order(const double* points, const uint64_t* elements, int64_t nelem, int nodeperelem, int ndim, int64_t nnode, int64_t* perm,
+                 void* stream) {
+    if (!points || (nelem > 0 && (!elements || !perm)) || nodeperelem < 1 || (ndim != 2 && ndim != 3) || nnode < 1) {
+        set_error("bad argument");
+        return FL_ERR_INVALID;
+    }
+    return launch_sfc_order(points, reinterpret_cast<const int64_t*>(elements), nelem, nodeperelem, ndim, nnode, perm, (cudaStream_t)stream);
 }
 
 int fl_measure_fp64_peak(int use_dmma, int iters, double* tflops_host) {

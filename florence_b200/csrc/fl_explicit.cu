@@ -187,68 +187,159 @@ __global__ void gather_nodes_kernel(const int64_t* __restrict__ adj_ptr, const i
     for (int i = 0; i < NV; ++i) T[n * NV + i] = acc[i];
 }
 
+// order-preserving map double -> int64 (signed compare), so that the running maximum of a vector can be kept with atomicMax
+__device__ __forceinline__ long long ordered_key(double v) {
+    const long long b = __double_as_longlong(v);
+    return b >= 0 ? b : (b ^ 0x7FFFFFFFFFFFFFFFLL);
+}
+__device__ __forceinline__ double key_to_double(long long k) {
+    return __longlong_as_double(k >= 0 ? k : (k ^ 0x7FFFFFFFFFFFFFFFLL));
+}
+
 // Central-difference update of one node (mechanics, lumped mass).  Written with explicit rounding so that the result is
 // the one numpy produces for ExplicitStructuralDynamicIntegrator.py:131-157 given the same T:
 //   R = (fs*F - T) + (((2/dt^2) M) U0 - ((1/dt^2) M) U00);  U = ((dt^2) (1/M)) R;  Eulerx = (X + U) + IncDirichlet
+// FUSED: T of the node is reduced here from the per-element tractions (ascending element order); for a node on a partition
+// interface (iface_slot[n] >= 0) the reduced force is instead read from T_iface, where the partial sums of all ranks sharing the
+// node have been added in ascending rank order (Assembly.py:1352-1354 `T_all[pnodes] += T_p`, made order-deterministic).
+// growth (2 x int64, optional): running signed maxima of the new U and of the previous U0 -- the operands of the reference's
+// blow-up test `abs(U.max() / (U0.max() + 1e-14)) > tol` (:175-180), evaluated by growth_check_kernel once the grid has finished.
 template <int D, bool FUSED>
 __global__ void explicit_update_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
-                                       const double* __restrict__ te, int64_t nnode, double dt, double fs, const double* __restrict__ M,
-                                       const double* __restrict__ fext, const uint8_t* __restrict__ fixed,
+                                       const double* __restrict__ te, int64_t nnode, double dt, double fs, double ds,
+                                       const double* __restrict__ M, const double* __restrict__ fext, const uint8_t* __restrict__ fixed,
                                        const double* __restrict__ inc_dir, const double* __restrict__ X, double* __restrict__ T,
-                                       int write_T, double* __restrict__ U0, double* __restrict__ U00, double* __restrict__ Eulerx,
-                                       int32_t* __restrict__ nan_flag, const Contact contact) {
+                                       int write_T, const int32_t* __restrict__ iface_slot, const double* __restrict__ T_iface,
+                                       double* __restrict__ U0, double* __restrict__ U00, double* __restrict__ Eulerx,
+                                       int32_t* __restrict__ nan_flag, long long* __restrict__ growth, const Contact contact) {
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (n >= nnode) return;
-    double t[D];
-    if (FUSED) {
+    const bool live = n < nnode;
+    double umax = -INFINITY, u0max = -INFINITY;
+    if (live) {
+        double t[D];
+        if (FUSED) {
+            const int slot = iface_slot ? iface_slot[n] : -1;
+            if (slot >= 0) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) t[i] = 0.0;
-        const int64_t k1 = adj_ptr[n + 1];
-        for (int64_t k = adj_ptr[n]; k < k1; ++k) {
-            const int64_t idx = adj_idx[k];
+                for (int i = 0; i < D; ++i) t[i] = T_iface[(int64_t)slot * D + i];
+            } else {
 #pragma unroll
-            for (int i = 0; i < D; ++i) t[i] += te[idx * D + i];
-        }
-        // TractionForces += contact tractions evaluated at the geometry the element forces were computed on
-        // (ExplicitStructuralDynamicIntegrator.py:190-197); a caller-supplied T (FUSED = false) already contains them
-        if (contact.surf && contact.surf[n]) {
-            double xo[D], fc[D];
+                for (int i = 0; i < D; ++i) t[i] = 0.0;
+                const int64_t k1 = adj_ptr[n + 1];
+                for (int64_t k = adj_ptr[n]; k < k1; ++k) {
+                    const int64_t idx = adj_idx[k];
 #pragma unroll
-            for (int i = 0; i < D; ++i) xo[i] = Eulerx[n * D + i];
-            if (contact_force<D>(contact, xo, fc)) {
-#pragma unroll
-                for (int i = 0; i < D; ++i) t[i] = __dadd_rn(t[i], fc[i]);
+                    for (int i = 0; i < D; ++i) t[i] += te[idx * D + i];
+                }
             }
+            // TractionForces += contact tractions evaluated at the geometry the element forces were computed on
+            // (ExplicitStructuralDynamicIntegrator.py:190-197); a caller-supplied T (FUSED = false) already contains them
+            if (contact.surf && contact.surf[n]) {
+                double xo[D], fc[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) xo[i] = Eulerx[n * D + i];
+                if (contact_force<D>(contact, xo, fc)) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) t[i] = __dadd_rn(t[i], fc[i]);
+                }
+            }
+            if (write_T) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) T[n * D + i] = t[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) t[i] = T[n * D + i];
         }
-        if (write_T) {
+        const double dt2 = __dmul_rn(dt, dt);
+        const double c2 = 2. / dt2, c1 = 1. / dt2;
+        bool bad = false;
 #pragma unroll
-            for (int i = 0; i < D; ++i) T[n * D + i] = t[i];
+        for (int i = 0; i < D; ++i) {
+            const int64_t q = n * D + i;
+            const double m = M[q], u0 = U0[q], u00 = U00[q];
+            const double f = fext ? __dmul_rn(fext[q], fs) : 0.0;
+            double R = __dadd_rn(f, -t[i]);
+            const double inert = __dadd_rn(__dmul_rn(__dmul_rn(c2, m), u0), -__dmul_rn(__dmul_rn(c1, m), u00));
+            R = __dadd_rn(R, inert);
+            double U = __dmul_rn(__dmul_rn(dt2, 1.0 / m), R);
+            const bool fx = fixed && fixed[q];
+            if (fx) U = 0.0;
+            const double incd = (fx && inc_dir) ? __dmul_rn(inc_dir[q], ds) : 0.0;
+            Eulerx[q] = __dadd_rn(__dadd_rn(X[q], U), incd);
+            U00[q] = u0;
+            U0[q] = U;
+            bad |= (U != U);
+            umax = fmax(umax, U);
+            u0max = fmax(u0max, u0);
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < D; ++i) t[i] = T[n * D + i];
+        if (bad) atomicOr(nan_flag, 1);
     }
-    const double dt2 = __dmul_rn(dt, dt);
-    const double c2 = 2. / dt2, c1 = 1. / dt2;
-    bool bad = false;
+    if (growth) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        const int64_t q = n * D + i;
-        const double m = M[q], u0 = U0[q], u00 = U00[q];
-        const double f = fext ? __dmul_rn(fext[q], fs) : 0.0;
-        double R = __dadd_rn(f, -t[i]);
-        const double inert = __dadd_rn(__dmul_rn(__dmul_rn(c2, m), u0), -__dmul_rn(__dmul_rn(c1, m), u00));
-        R = __dadd_rn(R, inert);
-        double U = __dmul_rn(__dmul_rn(dt2, 1.0 / m), R);
-        const bool fx = fixed && fixed[q];
-        if (fx) U = 0.0;
-        const double incd = (fx && inc_dir) ? inc_dir[q] : 0.0;
-        Eulerx[q] = __dadd_rn(__dadd_rn(X[q], U), incd);
-        U00[q] = u0;
-        U0[q] = U;
-        bad |= (U != U);
+        for (int o = 16; o > 0; o >>= 1) {
+            umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+            u0max = fmax(u0max, __shfl_xor_sync(0xffffffffu, u0max, o));
+        }
+        if ((threadIdx.x & 31) == 0 && umax > -INFINITY) {
+            atomicMax(growth, ordered_key(umax));
+            atomicMax(growth + 1, ordered_key(u0max));
+        }
     }
-    if (bad) atomicExch(nan_flag, 1);
+}
+
+// The reference's blow-up test (ExplicitStructuralDynamicIntegrator.py:175-180) on the maxima collected by the update kernel:
+// tol = 1e200 before increment 5, 10 afterwards.  status[0] |= 2 and status[1] = increment at the first detection (a NaN sets
+// bit 0 in the update kernel; its increment is recorded here as well).  The maxima are reset for the next step.
+__global__ void growth_check_kernel(long long* __restrict__ growth, long long increment, int32_t* __restrict__ status) {
+    const double umax = key_to_double(growth[0]), u0max = key_to_double(growth[1]);
+    const double tol = increment < 5 ? 1e200 : 10.0;
+    int32_t s = status[0];
+    if (fabs(umax / (u0max + 1e-14)) > tol) s |= 2;
+    if (s != 0 && status[1] == 0) status[1] = (int32_t)increment;
+    status[0] = s;
+    growth[0] = growth[1] = (long long)0x8000000000000000ULL;
+}
+
+// buf[k] = sum over the (element, local node) visits of node ids[k] (ascending element order) of the per-element tractions:
+// gather_nodes_kernel restricted to a node list, written densely -- the partial interface forces a rank sends to its neighbours
+template <int NV>
+__global__ void gather_pack_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
+                                   const double* __restrict__ te, const int32_t* __restrict__ ids, int64_t n, double* __restrict__ buf) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t node = ids[k];
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    const int64_t k1 = adj_ptr[node + 1];
+    for (int64_t q = adj_ptr[node]; q < k1; ++q) {
+        const int64_t idx = adj_idx[q];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] += te[idx * NV + i];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) buf[k * NV + i] = acc[i];
+}
+
+int launch_gather_pack(fl_handle* h, int nvar, const double* te, const int32_t* ids, int64_t n, double* buf, cudaStream_t st) {
+    if (n == 0) return FL_OK;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    switch (nvar) {
+        case 1: gather_pack_kernel<1><<<blocks, 128, 0, st>>>(h->adj_ptr, h->adj_idx, te, ids, n, buf); break;
+        case 2: gather_pack_kernel<2><<<blocks, 128, 0, st>>>(h->adj_ptr, h->adj_idx, te, ids, n, buf); break;
+        case 3: gather_pack_kernel<3><<<blocks, 128, 0, st>>>(h->adj_ptr, h->adj_idx, te, ids, n, buf); break;
+        case 4: gather_pack_kernel<4><<<blocks, 128, 0, st>>>(h->adj_ptr, h->adj_idx, te, ids, n, buf); break;
+        default: set_error("nvar=%d unsupported", nvar); return FL_ERR_INVALID;
+    }
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+int launch_growth_check(int64_t* growth, int64_t increment, int32_t* status, cudaStream_t st) {
+    growth_check_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(growth), (long long)increment, status);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -285,10 +376,12 @@ static int launch_expl(fl_handle* h, const double* Eulerx, const double* Eulerp,
     int occ = 1;
     FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EXPL_THREADS, smem));
     if (occ < 1) occ = 1;
-    const int64_t nbatch = (h->nelem + EB - 1) / EB;
+    const int64_t e0 = h->el0, ne = (h->el1 >= 0 ? h->el1 : h->nelem) - e0;   // element range of the call (fl_explicit_forces)
+    const int64_t nbatch = (ne + EB - 1) / EB;
     const int grid = (int)(nbatch < (int64_t)occ * h->sm_count ? nbatch : (int64_t)occ * h->sm_count);
-    if (grid == 0) return FL_OK;
-    kern<<<grid, EXPL_THREADS, smem, st>>>(h->conn, h->points, Eulerx, Eulerp, h->jm, h->gw, h->nelem, npe, ng, ldg, EB, prm, te);
+    if (grid <= 0) return FL_OK;
+    kern<<<grid, EXPL_THREADS, smem, st>>>(h->conn + e0 * npe, h->points, Eulerx, Eulerp, h->jm, h->gw, ne, npe, ng, ldg, EB, prm,
+                                           te + e0 * npe * NV);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }
@@ -350,16 +443,18 @@ int launch_gather_nodes(fl_handle* h, int nvar, const double* te, double* T, cud
     return FL_OK;
 }
 
-int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, double dt, double fext_scale, const double* M,
-                           const double* fext, const uint8_t* fixed, const double* inc_dir, double* T, double* U0, double* U00,
-                           double* Eulerx, int32_t* nan_flag, cudaStream_t st) {
+int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, double dt, double fext_scale, double incd_scale,
+                           const double* M, const double* fext, const uint8_t* fixed, const double* inc_dir, double* T,
+                           const int32_t* iface_slot, const double* T_iface, double* U0, double* U00, double* Eulerx, int32_t* nan_flag,
+                           int64_t* growth, cudaStream_t st) {
     if (h->nnode == 0) return FL_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)((h->nnode + threads - 1) / threads);
     const int write_T = (fused_gather == 2);
-#define FL_UPD(D_, F_)                                                                                                     \
-    explicit_update_kernel<D_, F_><<<blocks, threads, 0, st>>>(h->adj_ptr, h->adj_idx, te, h->nnode, dt, fext_scale, M, fext, fixed, \
-                                                               inc_dir, h->points, T, write_T, U0, U00, Eulerx, nan_flag, h->contact)
+#define FL_UPD(D_, F_)                                                                                                          \
+    explicit_update_kernel<D_, F_><<<blocks, threads, 0, st>>>(h->adj_ptr, h->adj_idx, te, h->nnode, dt, fext_scale, incd_scale, M, fext, \
+                                                               fixed, inc_dir, h->points, T, write_T, iface_slot, T_iface, U0, U00, Eulerx,  \
+                                                               nan_flag, reinterpret_cast<long long*>(growth), h->contact)
     if (h->ndim == 3) {
         if (fused_gather) FL_UPD(3, true); else FL_UPD(3, false);
     } else {

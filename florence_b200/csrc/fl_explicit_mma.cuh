@@ -261,10 +261,11 @@ int launch_expl_mma(fl_handle* h, const double* Eulerx, const MatParams& prm, do
     int occ = 1;
     FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_THREADS, S::SMEM));
     if (occ < 1) occ = 1;
-    const int64_t nbatch = (h->nelem + NE - 1) / NE;
+    const int64_t e0 = h->el0, ne = (h->el1 >= 0 ? h->el1 : h->nelem) - e0;   // element range of the call (fl_explicit_forces)
+    const int64_t nbatch = (ne + NE - 1) / NE;
     const int grid = (int)(nbatch < (int64_t)occ * h->sm_count ? nbatch : (int64_t)occ * h->sm_count);
-    if (grid == 0) return FL_OK;
-    kern<<<grid, MMA_THREADS, S::SMEM, st>>>(h->conn, h->points, Eulerx, h->jm, h->gw, h->nelem, h->ldg, prm, te);
+    if (grid <= 0) return FL_OK;
+    kern<<<grid, MMA_THREADS, S::SMEM, st>>>(h->conn + e0 * NPE, h->points, Eulerx, h->jm, h->gw, ne, h->ldg, prm, te + e0 * NPE * 3);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }

@@ -86,7 +86,9 @@ struct fl_handle {
     // scratch (grown on demand)
     double* te = nullptr;  size_t te_bytes = 0;   // per-element traction buffer nelem*ndof
     double* ke = nullptr;  size_t ke_bytes = 0;   // per-element stiffness buffer nelem*ndof^2 (CSR mode)
-    int32_t* flag = nullptr;                       // device status word
+    int32_t* flag = nullptr;                       // device status: [0] bit 0 NaN, bit 1 growth blow-up; [1] increment of first detection
+    int64_t* growth = nullptr;                     // running maxima (ordered keys) of U and U0 for the blow-up test
+    int64_t el0 = 0, el1 = -1;                     // element range of the explicit force call in flight (el1 < 0: all)
     int sm_count = 148;
     int max_smem_optin = 0;
     int timing = 0;
@@ -106,9 +108,12 @@ int ensure_scratch(double** p, size_t* have, size_t need);
 int launch_explicit_elements(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation,
                              double* te, cudaStream_t st);
 int launch_gather_nodes(fl_handle* h, int nvar, const double* te, double* T, cudaStream_t st);
-int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, double dt, double fext_scale, const double* M,
-                           const double* fext, const uint8_t* fixed, const double* inc_dir, double* T, double* U0, double* U00,
-                           double* Eulerx, int32_t* nan_flag, cudaStream_t st);
+int launch_explicit_update(fl_handle* h, int fused_gather, const double* te, double dt, double fext_scale, double incd_scale,
+                           const double* M, const double* fext, const uint8_t* fixed, const double* inc_dir, double* T,
+                           const int32_t* iface_slot, const double* T_iface, double* U0, double* U00, double* Eulerx, int32_t* nan_flag,
+                           int64_t* growth, cudaStream_t st);
+int launch_gather_pack(fl_handle* h, int nvar, const double* te, const int32_t* ids, int64_t n, double* buf, cudaStream_t st);
+int launch_growth_check(int64_t* growth, int64_t increment, int32_t* status, cudaStream_t st);
 int launch_contact(fl_handle* h, const double* Eulerx, double* T, int accumulate, cudaStream_t st);
 // fl_implicit.cu
 int launch_implicit_elements(fl_handle* h, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation,
@@ -122,6 +127,12 @@ int launch_pattern_export(fl_handle* h, int nvar, int32_t* indptr, int32_t* indi
 int launch_data_indices(fl_handle* h, int nvar, int32_t* dl, int32_t* dg, cudaStream_t st);
 int launch_coo_indices(fl_handle* h, int nvar, int32_t* I, int32_t* J, cudaStream_t st);
 int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st);
+int launch_row_block_build(fl_handle* h, int nvar, const int32_t* owned, int64_t n_owned, int64_t* indptr_block, int64_t* nnz_host,
+                           cudaStream_t st);
+int launch_row_block_emit(fl_handle* h, int nvar, const double* V, const int32_t* owned, int64_t n_owned, const int64_t* node_map,
+                          const int64_t* indptr_block, int64_t* cols, double* vals, cudaStream_t st);
+int launch_sfc_order(const double* points, const int64_t* elements, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
+                     cudaStream_t st);
 // fl_dirichlet.cu
 void dirichlet_free(fl_handle* h);
 int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_out);

@@ -19,6 +19,18 @@
 
 namespace fl {
 
+// Set-up temporaries: released on every exit path (FL_CUDA_CHECK returns early on error)
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { release(); return cudaMalloc(&p, bytes > 0 ? bytes : 8); }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 __global__ void iota_kernel(int32_t* v, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) v[i] = (int32_t)i;
@@ -64,26 +76,24 @@ int build_adjacency(fl_handle* h) {
         FL_CUDA_CHECK(cudaMemset(h->adj_ptr, 0, sizeof(int64_t) * (h->nnode + 1)));
         return FL_OK;
     }
-    int32_t *keys_out = nullptr, *vals_in = nullptr;
-    void* tmp = nullptr;
+    DevBuf keys_out, vals_in, tmp, dmax;
     size_t tmp_bytes = 0;
-    FL_CUDA_CHECK(cudaMalloc(&keys_out, sizeof(int32_t) * nk));
-    FL_CUDA_CHECK(cudaMalloc(&vals_in, sizeof(int32_t) * nk));
-    iota_kernel<<<(unsigned)((nk + 255) / 256), 256>>>(vals_in, nk);
+    FL_CUDA_CHECK(keys_out.alloc(sizeof(int32_t) * nk));
+    FL_CUDA_CHECK(vals_in.alloc(sizeof(int32_t) * nk));
+    iota_kernel<<<(unsigned)((nk + 255) / 256), 256>>>(vals_in.as<int32_t>(), nk);
     int end_bit = 1;
     while (((int64_t)1 << end_bit) < h->nnode && end_bit < 32) ++end_bit;
     // stable LSD radix sort: equal node ids keep ascending flat index, i.e. ascending element number
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->conn, keys_out, vals_in, h->adj_idx, (int)nk, 0, end_bit);
-    FL_CUDA_CHECK(cudaMalloc(&tmp, tmp_bytes));
-    FL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, h->conn, keys_out, vals_in, h->adj_idx, (int)nk, 0, end_bit));
-    lower_bound_kernel<int32_t><<<(unsigned)((h->nnode + 256) / 256), 256>>>(keys_out, nk, 1, h->nnode, h->adj_ptr);
-    int* dmax = nullptr;
-    FL_CUDA_CHECK(cudaMalloc(&dmax, sizeof(int)));
-    FL_CUDA_CHECK(cudaMemset(dmax, 0, sizeof(int)));
-    max_diff_kernel<<<(unsigned)((h->nnode + 255) / 256), 256>>>(h->adj_ptr, h->nnode, dmax);
-    FL_CUDA_CHECK(cudaMemcpy(&h->max_adj, dmax, sizeof(int), cudaMemcpyDeviceToHost));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->conn, keys_out.as<int32_t>(), vals_in.as<int32_t>(), h->adj_idx, (int)nk, 0, end_bit);
+    FL_CUDA_CHECK(tmp.alloc(tmp_bytes));
+    FL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, h->conn, keys_out.as<int32_t>(), vals_in.as<int32_t>(), h->adj_idx, (int)nk, 0,
+                                                  end_bit));
+    lower_bound_kernel<int32_t><<<(unsigned)((h->nnode + 256) / 256), 256>>>(keys_out.as<int32_t>(), nk, 1, h->nnode, h->adj_ptr);
+    FL_CUDA_CHECK(dmax.alloc(sizeof(int)));
+    FL_CUDA_CHECK(cudaMemset(dmax.p, 0, sizeof(int)));
+    max_diff_kernel<<<(unsigned)((h->nnode + 255) / 256), 256>>>(h->adj_ptr, h->nnode, dmax.as<int>());
+    FL_CUDA_CHECK(cudaMemcpy(&h->max_adj, dmax.p, sizeof(int), cudaMemcpyDeviceToHost));
     FL_CUDA_CHECK(cudaGetLastError());
-    cudaFree(dmax); cudaFree(tmp); cudaFree(keys_out); cudaFree(vals_in);
     return FL_OK;
 }
 
@@ -130,47 +140,60 @@ int pattern_build(fl_handle* h) {
         set_error("empty mesh has no sparsity pattern");
         return FL_ERR_INVALID;
     }
-    int64_t *keys = nullptr, *keys_sorted = nullptr, *uniq = nullptr, *d_num = nullptr;
-    void* tmp = nullptr;
+    // Memory: two int64 key arrays of nelem*npe^2 entries + the radix sort's temporary.  Every mesh whose CSR values and K_e
+    // scratch fit the device also fits this (the keys are 16 of the 8*nvar^2 + ... bytes per node pair the assembly itself needs).
+    DevBuf keys, keys_sorted, d_num, tmp, dmax;
     size_t tb1 = 0, tb2 = 0;
-    FL_CUDA_CHECK(cudaMalloc(&keys, sizeof(int64_t) * total));
-    FL_CUDA_CHECK(cudaMalloc(&keys_sorted, sizeof(int64_t) * total));
-    pair_keys_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->conn, h->nelem, npe, h->nnode, keys);
+    FL_CUDA_CHECK(keys.alloc(sizeof(int64_t) * total));
+    FL_CUDA_CHECK(keys_sorted.alloc(sizeof(int64_t) * total));
+    pair_keys_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->conn, h->nelem, npe, h->nnode, keys.as<int64_t>());
     int end_bit = 1;
     while (end_bit < 63 && ((int64_t)1 << end_bit) < h->nnode * h->nnode) ++end_bit;
-    cub::DeviceRadixSort::SortKeys(nullptr, tb1, keys, keys_sorted, total, 0, end_bit);
-    FL_CUDA_CHECK(cudaMalloc(&tmp, tb1));
-    FL_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tb1, keys, keys_sorted, total, 0, end_bit));
-    cudaFree(tmp); tmp = nullptr;
-    uniq = keys;  // reuse
-    FL_CUDA_CHECK(cudaMalloc(&d_num, sizeof(int64_t)));
-    cub::DeviceSelect::Unique(nullptr, tb2, keys_sorted, uniq, d_num, total);
-    FL_CUDA_CHECK(cudaMalloc(&tmp, tb2));
-    FL_CUDA_CHECK(cub::DeviceSelect::Unique(tmp, tb2, keys_sorted, uniq, d_num, total));
-    FL_CUDA_CHECK(cudaMemcpy(&p.nnzb, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost));
-    cudaFree(tmp); cudaFree(d_num); cudaFree(keys_sorted);
-    FL_CUDA_CHECK(cudaMalloc(&p.nbr_ptr, sizeof(int64_t) * (h->nnode + 1)));
-    FL_CUDA_CHECK(cudaMalloc(&p.nbr_idx, sizeof(int32_t) * p.nnzb));
+    cub::DeviceRadixSort::SortKeys(nullptr, tb1, keys.as<int64_t>(), keys_sorted.as<int64_t>(), total, 0, end_bit);
+    FL_CUDA_CHECK(tmp.alloc(tb1));
+    FL_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp.p, tb1, keys.as<int64_t>(), keys_sorted.as<int64_t>(), total, 0, end_bit));
+    tmp.release();
+    int64_t* uniq = keys.as<int64_t>();  // reuse
+    FL_CUDA_CHECK(d_num.alloc(sizeof(int64_t)));
+    cub::DeviceSelect::Unique(nullptr, tb2, keys_sorted.as<int64_t>(), uniq, d_num.as<int64_t>(), total);
+    FL_CUDA_CHECK(tmp.alloc(tb2));
+    FL_CUDA_CHECK(cub::DeviceSelect::Unique(tmp.p, tb2, keys_sorted.as<int64_t>(), uniq, d_num.as<int64_t>(), total));
+    FL_CUDA_CHECK(cudaMemcpy(&p.nnzb, d_num.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    tmp.release(); d_num.release(); keys_sorted.release();
+    auto fail = [&](int code) {   // leave the handle without a half-built pattern
+        cudaFree(p.nbr_ptr); cudaFree(p.nbr_idx); cudaFree(p.rank); cudaFree(p.rank_adj);
+        p = Pattern();
+        return code;
+    };
+#define FL_PTRY(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                            \
+            return fail(FL_ERR_CUDA);                                                             \
+        }                                                                                         \
+    } while (0)
+    FL_PTRY(cudaMalloc(&p.nbr_ptr, sizeof(int64_t) * (h->nnode + 1)));
+    FL_PTRY(cudaMalloc(&p.nbr_idx, sizeof(int32_t) * p.nnzb));
     lower_bound_kernel<int64_t><<<(unsigned)((h->nnode + 256) / 256), 256>>>(uniq, p.nnzb, h->nnode, h->nnode, p.nbr_ptr);
     split_keys_kernel<<<(unsigned)((p.nnzb + 255) / 256), 256>>>(uniq, p.nnzb, h->nnode, p.nbr_idx);
-    FL_CUDA_CHECK(cudaDeviceSynchronize());
-    cudaFree(keys);
-    int* dmax = nullptr;
-    FL_CUDA_CHECK(cudaMalloc(&dmax, sizeof(int)));
-    FL_CUDA_CHECK(cudaMemset(dmax, 0, sizeof(int)));
-    max_diff_kernel<<<(unsigned)((h->nnode + 255) / 256), 256>>>(p.nbr_ptr, h->nnode, dmax);
-    FL_CUDA_CHECK(cudaMemcpy(&p.max_cnt, dmax, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(dmax);
+    FL_PTRY(cudaDeviceSynchronize());
+    keys.release();
+    FL_PTRY(dmax.alloc(sizeof(int)));
+    FL_PTRY(cudaMemset(dmax.p, 0, sizeof(int)));
+    max_diff_kernel<<<(unsigned)((h->nnode + 255) / 256), 256>>>(p.nbr_ptr, h->nnode, dmax.as<int>());
+    FL_PTRY(cudaMemcpy(&p.max_cnt, dmax.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (p.max_cnt >= 65536) {
         set_error("a node with %d neighbours exceeds the uint16 rank map", p.max_cnt);
-        return FL_ERR_UNSUPPORTED;
+        return fail(FL_ERR_UNSUPPORTED);
     }
-    FL_CUDA_CHECK(cudaMalloc(&p.rank, sizeof(uint16_t) * total));
+    FL_PTRY(cudaMalloc(&p.rank, sizeof(uint16_t) * total));
     rank_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->conn, h->nelem, npe, p.nbr_ptr, p.nbr_idx, p.rank);
-    FL_CUDA_CHECK(cudaMalloc(&p.rank_adj, sizeof(uint16_t) * (total > 0 ? total : 1)));
+    FL_PTRY(cudaMalloc(&p.rank_adj, sizeof(uint16_t) * (total > 0 ? total : 1)));
     reorder_rank_kernel<<<(unsigned)((total + 255) / 256), 256>>>(p.rank, h->adj_idx, h->nelem * npe, npe, p.rank_adj);
-    FL_CUDA_CHECK(cudaGetLastError());
-    FL_CUDA_CHECK(cudaDeviceSynchronize());
+    FL_PTRY(cudaGetLastError());
+    FL_PTRY(cudaDeviceSynchronize());
+#undef FL_PTRY
     return FL_OK;
 }
 
@@ -541,6 +564,157 @@ int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaS
         case 4: return launch_csr_gather_NV<4>(h, ke, V, st);
         default: set_error("nvar=%d unsupported", nvar); return FL_ERR_INVALID;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ owned CSR row blocks
+// "Each rank emits the CSR row block it owns": the rows of the owned nodes of a locally assembled matrix, compacted, with the
+// column indices translated from local to GLOBAL dof numbers (Assembly.py:1000-1041 does this on the parent with the per-partition
+// `partitioned_maps`).  The nvar rows of a node are contiguous in V, so the values are a concatenation of contiguous runs.
+__global__ void row_block_counts_kernel(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ owned, int64_t n_owned, int nvar,
+                                        int64_t* __restrict__ cnt) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k > n_owned) return;
+    cnt[k] = k < n_owned ? (nbr_ptr[owned[k] + 1] - nbr_ptr[owned[k]]) * nvar * nvar : 0;
+}
+
+__global__ void row_block_indptr_kernel(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ owned, int64_t n_owned, int nvar,
+                                        const int64_t* __restrict__ node_off, int64_t* __restrict__ indptr) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k > n_owned) return;
+    if (k == n_owned) { indptr[n_owned * nvar] = node_off[n_owned]; return; }
+    const int64_t w = (nbr_ptr[owned[k] + 1] - nbr_ptr[owned[k]]) * nvar;
+    for (int i = 0; i < nvar; ++i) indptr[k * nvar + i] = node_off[k] + i * w;
+}
+
+__global__ void row_block_emit_kernel(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ owned,
+                                      int64_t n_owned, int nvar, const int64_t* __restrict__ node_map, const int64_t* __restrict__ indptr,
+                                      const double* __restrict__ V, int64_t* __restrict__ cols, double* __restrict__ vals) {
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n_owned) return;
+    const int64_t node = owned[k], p0 = nbr_ptr[node];
+    const int64_t w = (nbr_ptr[node + 1] - p0) * nvar;
+    const int64_t src = p0 * nvar * nvar, dst = indptr[k * nvar];
+    for (int64_t t = lane; t < nvar * w; t += 32) {
+        const int64_t c = t % w;
+        const int64_t q = c / nvar;
+        vals[dst + t] = V[src + t];
+        cols[dst + t] = node_map[nbr_idx[p0 + q]] * nvar + (c - q * nvar);
+    }
+}
+
+int launch_row_block_build(fl_handle* h, int nvar, const int32_t* owned, int64_t n_owned, int64_t* indptr_block, int64_t* nnz_host,
+                           cudaStream_t st) {
+    const Pattern& p = h->pat;
+    if (!p.nbr_ptr) { set_error("fl_pattern_build has not been called"); return FL_ERR_STATE; }
+    DevBuf cnt, off, tmp;
+    FL_CUDA_CHECK(cnt.alloc(sizeof(int64_t) * (n_owned + 1)));
+    FL_CUDA_CHECK(off.alloc(sizeof(int64_t) * (n_owned + 1)));
+    const unsigned blocks = (unsigned)((n_owned + 256) / 256);
+    row_block_counts_kernel<<<blocks, 256, 0, st>>>(p.nbr_ptr, owned, n_owned, nvar, cnt.as<int64_t>());
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.as<int64_t>(), off.as<int64_t>(), (int)(n_owned + 1), st);
+    FL_CUDA_CHECK(tmp.alloc(tb));
+    FL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.as<int64_t>(), off.as<int64_t>(), (int)(n_owned + 1), st));
+    row_block_indptr_kernel<<<blocks, 256, 0, st>>>(p.nbr_ptr, owned, n_owned, nvar, off.as<int64_t>(), indptr_block);
+    FL_CUDA_CHECK(cudaGetLastError());
+    if (nnz_host) FL_CUDA_CHECK(cudaMemcpyAsync(nnz_host, off.as<int64_t>() + n_owned, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FL_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FL_OK;
+}
+
+int launch_row_block_emit(fl_handle* h, int nvar, const double* V, const int32_t* owned, int64_t n_owned, const int64_t* node_map,
+                          const int64_t* indptr_block, int64_t* cols, double* vals, cudaStream_t st) {
+    const Pattern& p = h->pat;
+    if (!p.nbr_ptr) { set_error("fl_pattern_build has not been called"); return FL_ERR_STATE; }
+    if (n_owned == 0) return FL_OK;
+    const int64_t threads = n_owned * 32;
+    row_block_emit_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p.nbr_ptr, p.nbr_idx, owned, n_owned, nvar, node_map, indptr_block, V,
+                                                                             cols, vals);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ space-filling-curve element order
+// Morton (Z-order) key of the element centroid, 21 bits per axis, relative to the bounding box of the nodes.  Sorting the elements
+// by this key before cutting them into contiguous blocks (Mesh.Partition, Mesh.py:7403: np.array_split of the element range) gives
+// compact blocks -- small interfaces -- whatever order the mesh file came in.  Every operation is an individually rounded IEEE
+// operation so that the host twin (partition.sfc_order on numpy arrays) produces the same keys bit for bit.
+__device__ __forceinline__ long long okey(double v) {
+    const long long b = __double_as_longlong(v);
+    return b >= 0 ? b : (b ^ 0x7FFFFFFFFFFFFFFFLL);
+}
+__device__ __forceinline__ double okey_inv(long long k) { return __longlong_as_double(k >= 0 ? k : (k ^ 0x7FFFFFFFFFFFFFFFLL)); }
+
+__global__ void bbox_kernel(const double* __restrict__ pts, int64_t nnode, int D, long long* __restrict__ box /* [2*D]: lo keys, hi keys */) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int k = 0; k < D; ++k) {
+        double lo = n < nnode ? pts[n * D + k] : INFINITY, hi = n < nnode ? pts[n * D + k] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0 && lo <= hi) {
+            atomicMin(box + k, okey(lo));
+            atomicMax(box + D + k, okey(hi));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread3(uint64_t x) {   // 21 bits -> every third bit
+    x &= 0x1FFFFFULL;
+    x = (x | x << 32) & 0x1F00000000FFFFULL;
+    x = (x | x << 16) & 0x1F0000FF0000FFULL;
+    x = (x | x << 8) & 0x100F00F00F00F00FULL;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+
+__global__ void morton_keys_kernel(const double* __restrict__ pts, const int64_t* __restrict__ els, int64_t nelem, int npe, int D,
+                                   const long long* __restrict__ box, uint64_t* __restrict__ keys, int64_t* __restrict__ iota) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    uint64_t key = 0;
+    for (int k = 0; k < D; ++k) {
+        double c = 0.0;
+        for (int a = 0; a < npe; ++a) c = __dadd_rn(c, pts[els[e * npe + a] * D + k]);
+        c = __ddiv_rn(c, (double)npe);
+        const double lo = okey_inv(box[k]), hi = okey_inv(box[D + k]);
+        const double span = __dadd_rn(hi, -lo);
+        double u = span > 0.0 ? __ddiv_rn(__dadd_rn(c, -lo), span) : 0.0;
+        u = __dmul_rn(u, 2097152.0);
+        int64_t q = (int64_t)u;
+        q = q < 0 ? 0 : (q > 2097151 ? 2097151 : q);
+        key |= spread3((uint64_t)q) << k;
+    }
+    keys[e] = key;
+    iota[e] = e;
+}
+
+int launch_sfc_order(const double* points, const int64_t* elements, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
+                     cudaStream_t st) {
+    if (nelem == 0) return FL_OK;
+    DevBuf box, keys, keys_out, iota, tmp;
+    FL_CUDA_CHECK(box.alloc(sizeof(long long) * 6));
+    long long init[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < ndim; ++k) { init[k] = INT64_MAX; init[ndim + k] = INT64_MIN; }
+    FL_CUDA_CHECK(cudaMemcpyAsync(box.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    FL_CUDA_CHECK(cudaStreamSynchronize(st));   // `init` is a stack array
+    bbox_kernel<<<(unsigned)((nnode + 255) / 256), 256, 0, st>>>(points, nnode, ndim, box.as<long long>());
+    FL_CUDA_CHECK(keys.alloc(sizeof(uint64_t) * nelem));
+    FL_CUDA_CHECK(keys_out.alloc(sizeof(uint64_t) * nelem));
+    FL_CUDA_CHECK(iota.alloc(sizeof(int64_t) * nelem));
+    morton_keys_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>(points, elements, nelem, npe, ndim, box.as<long long>(),
+                                                                        keys.as<uint64_t>(), iota.as<int64_t>());
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.as<uint64_t>(), keys_out.as<uint64_t>(), iota.as<int64_t>(), perm, nelem, 0, 63, st);
+    FL_CUDA_CHECK(tmp.alloc(tb));
+    // stable: elements with equal keys keep their original relative order
+    FL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.as<uint64_t>(), keys_out.as<uint64_t>(), iota.as<int64_t>(), perm, nelem, 0, 63, st));
+    FL_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FL_OK;
 }
 
 }  // namespace fl

@@ -146,26 +146,80 @@ int fl_assemble_mass(fl_handle *h, double rho, int nvar, int mass_type, int mode
  *   U00 <- U0 <- U ; T = internal force(Eulerx)
  * F_ext(inc) = fext_scale0 + (inc) * fext_scale_step times `fext` (ramp loading, :121-128).  fixed_mask: uint8, 1 = Dirichlet dof;
  * inc_dirichlet (nnode*ndim, may be NULL): prescribed displacement of fixed dofs.  T holds the internal force of the current
- * Eulerx on entry and exit.  status_host[0] is set to 1 if a NaN was produced (blow-up test, :175-180). */
+ * Eulerx on entry and exit. */
 typedef struct {
     double dt;
-    double fext_scale0, fext_scale_step;
+    double fext_scale0, fext_scale_step;   /* F_ext(inc)       = (fext_scale0 + inc * fext_scale_step) * fext           (:121-128) */
+    double incd_scale0, incd_scale_step;   /* IncDirichlet(inc) = (incd_scale0 + inc * incd_scale_step) * inc_dirichlet  (:101-108) */
     int64_t increment, nsteps;
 } fl_explicit_ctrl;
+/* status_host (2 x int32, may be NULL): [0] bit 0 = a NaN was produced, bit 1 = abs(U.max() / (U0.max() + 1e-14)) exceeded the
+ * reference's tolerance (1e200 before increment 5, 10 afterwards, :175-180); [1] = increment of the first detection. */
 int fl_explicit_steps(fl_handle *h, const fl_material *mat, const fl_explicit_ctrl *ctrl, const double *M, const double *fext,
                       const uint8_t *fixed_mask, const double *inc_dirichlet, double *U0, double *U00, double *Eulerx, double *T,
                       int32_t *status_host, void *stream);
 
-/* Interface exchange support for element-partitioned meshes (replaces the whole-vector Bcast/Reduce of
- * Florence/FiniteElements/Assembly/Assembly.py:1135-1167): gather/scatter-add of T at a list of local node ids. */
+/* ---- Element-partitioned runs: one process per GPU replaces the reference's process pool / MPI launchers
+ * (Florence/FiniteElements/Assembly/Assembly.py:1126-1358).  Each rank owns a contiguous block of elements (Mesh.Partition,
+ * Florence/MeshGeneration/Mesh.py:7395-7447) and every node it touches; only the partial internal forces of INTERFACE nodes
+ * cross NVLink (the reference broadcasts the whole Eulerx and reduces the whole T every step, Assembly.py:1153-1167). */
+
+/* gather / scatter of a nodal vector at a list of local node ids: T[node_ids] -> buf, T[node_ids] += buf, T[node_ids] = buf */
 int fl_pack_nodes(const double *T, const int32_t *node_ids, int64_t n, int nvar, double *buf, void *stream);
 int fl_unpack_add_nodes(double *T, const int32_t *node_ids, int64_t n, int nvar, const double *buf, void *stream);
+int fl_scatter_nodes(double *T, const int32_t *node_ids, int64_t n, int nvar, const double *buf, void *stream);
+/* out[k] (nvar doubles) = sum over j in [ptr[k], ptr[k+1]) of all[idx[j] .. idx[j]+nvar), added in list order.  The host layer
+ * lists the contributions of every rank sharing an interface node in ascending rank order, so all sharers compute bit-identical
+ * sums (`T_all[pnodes] += T_p`, Assembly.py:1352-1354, made independent of the summation order of the ranks). */
+int fl_sum_ordered(const double *all, const int64_t *ptr, const int64_t *idx, int64_t n, int nvar, double *out, void *stream);
 
-/* Split form of fl_explicit_steps for multi-GPU runs (force -> exchange -> update):
- * fl_explicit_update applies one central-difference update given the (already exchanged) internal force T. */
-int fl_explicit_update(fl_handle *h, double dt, double fext_scale, const double *M, const double *fext, const uint8_t *fixed_mask,
-                       const double *inc_dirichlet, const double *T, double *U0, double *U00, double *Eulerx, int32_t *nan_flag_dev,
-                       void *stream);
+/* Split form of fl_explicit_steps (mechanics): per step  update -> forces(interface elements) -> gather_pack -> [exchange, host layer]
+ * -> forces(remaining elements, overlapping the exchange) -> sum_ordered -> next update.
+ * fl_explicit_forces: per-element internal forces of elements [e0, e1) into the handle's scratch (the element kernel of
+ *   fl_assemble_explicit on a sub-range; _LowLevelAssemblyExplicit_DF_DPF_.h:458-717).
+ * fl_gather_pack_nodes: buf[k] = nodal sum of that scratch at node_ids[k] (ascending element order).
+ * fl_gather_nodes: the full nodal reduction T (nnode*nvar) of the scratch (RHSAssemblyNative.pyx:30-39). */
+int fl_explicit_forces(fl_handle *h, const double *Eulerx, const fl_material *mat, int64_t e0, int64_t e1, void *stream);
+int fl_gather_pack_nodes(fl_handle *h, int nvar, const int32_t *node_ids, int64_t n, double *buf, void *stream);
+int fl_gather_nodes(fl_handle *h, int nvar, double *T, void *stream);
+/* fl_explicit_update: one central-difference update (ExplicitStructuralDynamicIntegrator.py:131-157).
+ *   use_element_forces = 0: the internal force is the caller's T (already reduced and exchanged);
+ *   use_element_forces = 1: it is reduced here from the scratch of fl_explicit_forces, except at nodes with iface_slot[n] >= 0,
+ *     where T_iface[iface_slot[n]] (the rank-ordered interface sum) is used; write_T stores the reduced force in T.
+ *   status_dev (2 x int32) / growth_keys_dev (2 x int64, may be NULL): see fl_explicit_check. */
+typedef struct {
+    double dt, fext_scale, incd_scale;
+    const double *M, *fext;
+    const uint8_t *fixed_mask;
+    const double *inc_dirichlet;
+    double *T;
+    const int32_t *iface_slot;
+    const double *T_iface;
+    double *U0, *U00, *Eulerx;
+    int32_t *status_dev;
+    int64_t *growth_keys_dev;
+    int32_t use_element_forces, write_T;
+} fl_update_args;
+int fl_explicit_update(fl_handle *h, const fl_update_args *args, void *stream);
+/* Blow-up test of the explicit loop (:175-180) on the running maxima the update kernel left in growth_keys_dev (order-preserving
+ * int64 images of U.max() and U0.max(); initialise both to INT64_MIN; the host layer takes the MAX over ranks first):
+ * sets status_dev[0] bit 1 / status_dev[1] = increment and resets the maxima. */
+int fl_explicit_check(fl_handle *h, int64_t *growth_keys_dev, int64_t increment, int32_t *status_dev, void *stream);
+
+/* Implicit multi-GPU: "each rank emits the CSR row block it owns" (the reference sums per-partition triplets on
+ * the parent, Assembly.py:1000-1041).  owned_nodes: ascending local node ids owned by this rank; node_map: global node id of every
+ * local node.  fl_row_block_build writes the int64 row pointer of the block (n_owned*nvar+1 entries, starting at 0) and returns
+ * its nnz; fl_row_block_emit copies the owned rows of V (aligned with fl_pattern_export) and writes GLOBAL column dof numbers. */
+int fl_row_block_build(fl_handle *h, int nvar, const int32_t *owned_nodes, int64_t n_owned, int64_t *indptr_block,
+                       int64_t *nnz_block_host, void *stream);
+int fl_row_block_emit(fl_handle *h, int nvar, const double *V, const int32_t *owned_nodes, int64_t n_owned, const int64_t *node_map,
+                      const int64_t *indptr_block, int64_t *cols_global, double *vals, void *stream);
+
+/* Space-filling-curve element order (BASELINE north_star; Mesh.Partition cuts np.array_split(arange(nelem)), Mesh.py:7403, so the
+ * element order decides the interface size): perm (nelem int64) = elements sorted by the Morton key of their centroid, stable.
+ * points / elements are DEVICE arrays as in fl_mesh_desc. */
+int fl_sfc_order(const double *points, const uint64_t *elements, int64_t nelem, int nodeperelem, int ndim, int64_t nnode,
+                 int64_t *perm, void *stream);
 
 /* Tuning switches (for tests and A/B timing): option 0 = use the tensor-core (DMMA) explicit kernels for
  * hex8/hex27 (default 1); option 1 = use the DMMA implicit kernels for hex27/hex64 (default 1); option 2 = use the

@@ -316,10 +316,93 @@ def gen_explicit(out):
     print("explicit", sol.sol.shape, np.abs(sol.sol).max())
 
 
+def gen_explicit_rules(out):
+    """The save / termination rules of the reference's explicit integrator (ExplicitStructuralDynamicIntegrator.py:165-251), pinned by
+    running it: (a) save_frequency = 3, (b) a time step above the stability limit (the growth test `abs(U.max()/(U0.max()+1e-14)) > 10`
+    fires and TotalDisp is cut), (c) break_at_increment.  Same mesh, material and loading as gen_explicit; constant-vector ramp loading
+    (1-D applied_dirichlet, single-column NeumannForces) so that the device-resident chunked loop of the drop-in is what gets compared."""
+    ndim = 3
+    nsteps_all = {"sf3": 18, "blow": 40, "brk": 15}
+    for tag, nsteps in nsteps_all.items():
+        mesh = make_mesh("hex", 2, 2)
+        material, prm = material_of("NeoHookean", ndim)
+        material.has_low_level_dispatcher = False
+
+        def dirichlet(mesh):
+            bd = np.zeros((mesh.points.shape[0], 3)) + np.nan
+            bd[np.isclose(mesh.points[:, 2], 0), :] = 0.
+            bd[np.isclose(mesh.points[:, 2], mesh.points[:, 2].max()), 2] = 0.01
+            return bd
+
+        def neumann(mesh):
+            flags = np.zeros(mesh.faces.shape[0], dtype=np.uint8)
+            data = np.zeros((mesh.faces.shape[0], 3))
+            for i in range(mesh.faces.shape[0]):
+                avg = mesh.points[mesh.faces[i, :], :].mean(0)
+                if np.isclose(avg[0], mesh.points[:, 0].max()):
+                    data[i, 0] = 2.0e3
+                    flags[i] = True
+            return flags, data
+
+        bc = BoundaryCondition()
+        bc.SetDirichletCriteria(dirichlet, mesh)
+        bc.SetNeumannCriteria(neumann, mesh)
+        form = DisplacementFormulation(mesh)
+        h = 0.8 / 4
+        cfl = h / np.sqrt((prm["lamb"] + 2 * prm["mu"]) / 1100.0)
+        dt = (0.1 if tag != "blow" else 1.5) * cfl
+        kw = dict(total_time=dt * nsteps, number_of_load_increments=nsteps, analysis_type="dynamic", analysis_subtype="explicit",
+                  mass_type="lumped", optimise=False, print_incremental_log=False, report_log_level=0)
+        if tag == "sf3":
+            kw["memory_store_frequency"] = 3
+        if tag == "brk":
+            kw["break_at_increment"] = 9
+        fem_solver = FEMSolver(**kw)
+        from Florence.TimeIntegrators import ExplicitStructuralDynamicIntegrator as ESDI
+        rec = {}
+        orig = ESDI.Solver
+
+        def recording_solver(self, function_spaces, formulation, solver, TractionForces, M, NeumannForces, NodalForces, Residual,
+                             mesh_, TotalDisp, *a, **k):
+            rec["T0"] = np.array(TractionForces).ravel().copy()
+            rec["M"] = np.array(M).ravel().copy()
+            rec["NeumannForces"] = np.array(NeumannForces).copy()
+            rec["TotalDisp_shape"] = np.array(TotalDisp.shape)
+            return orig(self, function_spaces, formulation, solver, TractionForces, M, NeumannForces, NodalForces, Residual, mesh_,
+                        TotalDisp, *a, **k)
+        ESDI.Solver = recording_solver
+        try:
+            sol = fem_solver.Solve(formulation=form, mesh=mesh, material=material, boundary_condition=bc)
+        finally:
+            ESDI.Solver = orig
+        fs = form.function_spaces[1]
+        pre = "rule_%s_" % tag
+        if tag == "sf3":
+            out["rule_points"] = mesh.points
+            out["rule_elements"] = mesh.elements.astype(np.int64)
+            out["rule_faces"] = mesh.faces.astype(np.int64)
+            out["rule_Jm"] = fs.Jm
+            out["rule_AllGauss"] = fs.AllGauss
+            out["rule_Bases"] = fs.Bases
+            out["rule_prm"] = np.array([prm.get(k, 0.0) for k in ("mu", "mu1", "mu2", "mu3", "mue", "lamb", "eps_1", "eps_2", "eps_3", "eps_e")])
+            out["rule_columns_out"] = bc.columns_out
+            out["rule_applied_dirichlet"] = np.asarray(bc.applied_dirichlet)
+        out[pre + "nsteps"] = np.array(nsteps)
+        out[pre + "dt"] = np.array(dt)
+        out[pre + "TotalDisp"] = sol.sol
+        out[pre + "TotalDisp_shape_in"] = rec["TotalDisp_shape"]
+        out[pre + "number_of_load_increments"] = np.array(fem_solver.number_of_load_increments)
+        out[pre + "neumann"] = rec["NeumannForces"]
+        out[pre + "M"] = rec["M"]
+        out[pre + "T0"] = rec["T0"]
+        print(tag, "TotalDisp", sol.sol.shape, "allocated", rec["TotalDisp_shape"], "increments", fem_solver.number_of_load_increments,
+              "applied_dirichlet", np.asarray(bc.applied_dirichlet).shape, "neumann", rec["NeumannForces"].shape, np.abs(sol.sol).max())
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "materials", "assembly", "laplacian", "explicit"]
     gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, assembly_hi=gen_assembly_hi, laplacian=gen_laplacian,
-                explicit=gen_explicit)
+                explicit=gen_explicit, explicit_rules=gen_explicit_rules)
     for w in which:
         out = {}
         gens[w](out)

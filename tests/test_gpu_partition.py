@@ -61,18 +61,22 @@ def test_explicit_partial_forces_sum_to_the_global_force(p, n, world):
         Tsum[gl] += hl.assemble_explicit(x[part.node_map], None, mat, 0).cpu().numpy().reshape(-1, 3)
         Msum[gl] += hl.assemble_mass(1100.0, 3, "lumped").cpu().numpy().reshape(-1, 3)
         # the pack / unpack kernels of the interface exchange: packing then adding back doubles the shared entries only
-        pack, unpack_add = partition.device_pack_functions(hl)
+        import ctypes as C
+        from florence_b200._lib import check
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for other, ids in part.neighbours.items():
             ids_d = ids.to(hl.device)
             v = torch.arange(part.points.shape[0] * 3, dtype=torch.float64, device=hl.device)
             buf = torch.empty(ids.numel() * 3, dtype=torch.float64, device=hl.device)
-            pack(v, ids_d, buf)
+            check(hl.lib.fl_pack_nodes(C.c_void_p(v.data_ptr()), C.c_void_p(ids_d.data_ptr()), ids_d.numel(), 3, C.c_void_p(buf.data_ptr()), st))
             assert torch.equal(buf.view(-1, 3), v.view(-1, 3)[ids_d.long()])
             w = v.clone()
-            unpack_add(w, ids_d, buf)
+            check(hl.lib.fl_unpack_add_nodes(C.c_void_p(w.data_ptr()), C.c_void_p(ids_d.data_ptr()), ids_d.numel(), 3, C.c_void_p(buf.data_ptr()), st))
             expect = v.clone().view(-1, 3)
             expect[ids_d.long()] *= 2
             assert torch.equal(w.view(-1, 3), expect)
+            check(hl.lib.fl_scatter_nodes(C.c_void_p(w.data_ptr()), C.c_void_p(ids_d.data_ptr()), ids_d.numel(), 3, C.c_void_p(buf.data_ptr()), st))
+            assert torch.equal(w, v)
         hl.close()
     assert np.abs(Tsum - T).max() <= 1e-12 * np.abs(T).max()
     assert np.abs(Msum - M).max() <= 1e-13 * np.abs(M).max()

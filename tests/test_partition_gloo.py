@@ -57,12 +57,14 @@ def _worker(rank, world, port, kind, q):
         blocks = partition.element_blocks(els.shape[0], world)
         ref = np.array_split(np.arange(els.shape[0]), world)
         ok_blocks = all(b[0] == r[0] and b[1] == r[-1] + 1 for b, r in zip(blocks, ref))
-        q.put((rank, float(errT), float(errM), bool(ok_blocks), int(sum(v.numel() for v in part.neighbours.values()))))
+        Tn = Tt.numpy().reshape(-1, 3)
+        shared = {int(gl[i]): Tn[i].tobytes() for i in ex.U.numpy()}
+        q.put((rank, float(errT), float(errM), bool(ok_blocks), int(sum(v.numel() for v in part.neighbours.values())), shared))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,world", [("generic_tet", 2), ("slab_hex", 2), ("slab_hex", 3)])
+@pytest.mark.parametrize("kind,world", [("generic_tet", 2), ("generic_tet", 3), ("generic_tet", 4), ("slab_hex", 2), ("slab_hex", 3)])
 def test_partition_and_interface_exchange(kind, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -74,10 +76,20 @@ def test_partition_and_interface_exchange(kind, world):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, errT, errM, ok_blocks, nshared in res:
+    copies, most = {}, 0
+    for rank, errT, errM, ok_blocks, nshared, shared in res:
         assert errT < 1e-13 and errM < 1e-13, (rank, errT, errM)
         assert ok_blocks
         assert nshared > 0
+        for node, bits in shared.items():
+            copies.setdefault(node, []).append(bits)
+    # every rank that holds a shared node computed the same sum BIT FOR BIT (contributions are added in ascending rank order on
+    # all sharers), also where three or more ranks meet
+    for node, lst in copies.items():
+        assert len(lst) >= 2 and all(b == lst[0] for b in lst), node
+        most = max(most, len(lst))
+    if kind == "generic_tet" and world == 3:      # 144 tets in 3 blocks of 48: the cuts fall inside hex layers, 3 ranks meet at nodes
+        assert most >= 3
 
 
 def _row_worker(rank, world, port, q):
