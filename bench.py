@@ -6,11 +6,19 @@ elements, 1 367 631 nodes, implicit stiffness + residual assembled to CSR (requi
 computed).  One "step" = one full assembly (K values in CSR order + T) of the whole mesh.
   value : elements/s with the state already in HBM (CUDA events around K steps, max over ranks)
   e2e   : the same assembly through the reference-facing plug-in function with HOST numpy state in and HOST K values / T out
-  roofline / roofline_fp64 : dominant kernel by share of the step (CUDA events inside the library), the other kernels and the whole step
+  roofline : SURVEY.md 8(d)'s algorithmic bytes per element x elements / the device-timed step / the measured HBM peak -- the WHOLE
+             step (all kernels of one assembly), with the per-kernel figures under `kernels`; `traffic` is the ncu dram__bytes of
+             the same kernels from the capture named in `traffic_source` (null when no capture of this round exists)
+  roofline_fp64 : executed fp64 work of the element kernel against the DFMA peak measured in this run (builder-measured)
   cpu_baseline : the CPU restatement of the reference algorithm (oracle, -O3 -ffast-math) on a bounded sample, 1 core
-  explicit : secondary line for the metric's second half -- NeoHookean p=2 hex explicit dynamics, DOF-updates/s
+  explicit / explicit5a / explicit5b : the metric's second half -- explicit central-difference DOF-updates/s for config 3
+             (NeoHookean hex27) and config 5 (MooneyRivlin hex8 / hex27), 200^3 elements per GPU (weak); explicit3_strong (N > 1):
+             config 3's 200^3 mesh split over the ranks
+  hiorder : config 4 (EM_108 hex64 Newton-step assembly) against the measured DMMA peak;  poisson : config 1 (hex125 Laplacian)
 N > 1 (torchrun): weak scaling, every rank assembles its own slab (+1 halo layer of elements so the CSR rows of the nodes it
-owns are complete; no data-path collective); the explicit line exchanges interface forces over NCCL every step.
+owns are complete; no data-path collective) and emits the CSR row block it owns with global column numbers (values: a slice of
+V; columns and the all_gather'ed offsets belong to the pattern and are built once); the explicit lines exchange interface forces
+over NCCL every step, overlapped with the interior elements.
 `--impl reference` times the reference algorithm (oracle port) on all host cores instead.
 """
 import argparse
@@ -40,6 +48,8 @@ def parse():
     ap.add_argument("--no-hiorder", action="store_true")
     ap.add_argument("--hiorder-n", type=int, default=24, help="hexes per edge of the p=3 electro-mechanical Newton-step line (config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-poisson", action="store_true")
     return ap.parse_args()
 
 
@@ -183,6 +193,8 @@ def run_reference(args, rank, world):
                              "sample": "%d tet10 elements per step (slab %dx%dx%d of the %d^3 mesh), %d thread-pool blocks, CSR slot-map mode, per-block (V, T) "
                                        "summed on the parent; pattern + slot maps built once outside the timed region" % (nelem, n, n, nz, n, cores)},
             "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "steps_note": "CPU arm: at most 3 timed steps and 1 warm-up of a bounded slab sample whatever --steps/--warmup ask for "
+                          "(one step is ~1.4 s of all host cores; elements/s is size-independent here)",
             "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -208,6 +220,7 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     launches = 0
+    hbm_peak, peak_src = measured_peaks()
     # ------------------------------------------------------------------ implicit tet10 (config 2)
     n = args.n
     halo = 1 if (world > 1 and rank < world - 1) else 0
@@ -216,7 +229,6 @@ def run_b200(args, rank, world, local_rank):
     Bases, Jm, AG = flmesh.tables("tet", 2)
     nelem_local, nnode = els.shape[0], pts.shape[0]
     nelem_owned = 6 * n * n * n
-    h_edge = 1.0 / n
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     x = pts + 1e-3 * (2.0 * torch.rand(pts.shape, dtype=torch.float64, device=dev, generator=gen) - 1.0)
     h = backend.AssemblyHandle(pts, els, Jm, AG, Bases, device=dev)
@@ -225,18 +237,38 @@ def run_b200(args, rank, world, local_rank):
     V = torch.empty(nnz, dtype=torch.float64, device=dev)
     T = torch.empty(nnode * 3, dtype=torch.float64, device=dev)
     ndof = 30
+    # N > 1: the rows this rank owns (node planes of its own slab; the bottom plane belongs to the rank below, whose halo layer
+    # completes it), their global numbering and the position of the block in the global CSR (all_gather + exclusive scan, once)
+    row_info = None
+    if world > 1:
+        plane = (2 * n + 1) ** 2
+        p0, p1 = (1 if rank > 0 else 0), 2 * n + 1
+        owned = torch.arange(p0 * plane, p1 * plane, dtype=torch.int32, device=dev)
+        node_map = torch.arange(nnode, dtype=torch.int64, device=dev) + rank * 2 * n * plane
+        ipb, colsb, valsb = h.row_block(3, V, owned, node_map)
+        ro, no, tr, tn = partition.global_row_offsets(ipb.numel() - 1, int(ipb[-1]), device=dev)
+        row_info = {"row_block_emitted": True, "rows": int(ipb.numel() - 1), "nnz_block": int(ipb[-1]), "row_offset": ro, "nnz_offset": no,
+                    "global_rows": tr, "global_nnz": tn,
+                    "values": "zero-copy slice of V (owned node planes are a contiguous row range)" if valsb.data_ptr() != 0 and
+                              valsb.untyped_storage().data_ptr() == V.untyped_storage().data_ptr() else "compacted copy"}
+
+    def step():
+        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+        if world > 1:
+            h.row_block(3, V, owned, node_map)
+
     clocks = Clocks(local_rank)
     if rank == 0:
         clocks.start()
         time.sleep(1.0)   # nvidia-smi needs about a second before its first sample
     for _ in range(max(args.warmup, 3)):
-        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+        step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T))
+        step()
     e1.record()
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -271,20 +303,30 @@ def run_b200(args, rank, world, local_rank):
     # pre-seed the handle cache with the handle that already holds this mesh (same mesh arrays -> no re-upload)
     assembly._handle_cache[(assembly._array_key(pts_host), assembly._array_key(els_host), assembly._array_key(Jm))] = h
     func = assembly._LowLevelAssemblyDF__LinearElastic_
-    for _ in range(2):
-        Vh, Th = func(so, fs, fo, me, material, x_host, None)
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        Vh, Th = func(so, fs, fo, me, material, x_host, None)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    launches += 3 * (e2e_steps + 2)
-    e2e_value = nelem_owned * world * e2e_steps / e2e_s
+
+    def time_e2e():
+        for _ in range(2):
+            out = func(so, fs, fo, me, material, x_host, None)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = func(so, fs, fo, me, material, x_host, None)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0), out
+    # headline e2e: a Newton loop consumes K before it re-assembles, so it opts in to the pinned result ring
+    # (assembly.reuse_host_buffers); the default (every call returns freshly allocated arrays, as the reference does) is timed too
+    assembly.reuse_host_buffers(True)
+    e2e_s, (Vh, Th) = time_e2e()
+    assert np.array_equal(Vh, V.cpu().numpy()), "host path and device path disagree"
     h2d = x_host.nbytes
     d2h = Vh.nbytes + Th.nbytes
-    assert np.array_equal(Vh, V.cpu().numpy()), "host path and device path disagree"
+    assembly.reuse_host_buffers(False)
+    fresh_s, (Vf, Tf) = time_e2e()
+    assert np.array_equal(Vf, Vh) and not np.shares_memory(Vf, Vh)
+    del Vf, Tf
+    launches += 6 * (e2e_steps + 2)
+    e2e_value = nelem_owned * world * e2e_steps / e2e_s
 
     # ------------------------------------------------------------------ the same Newton-iteration assembly with K kept on the device
     # (SURVEY.md 8f.1): host state in -> plug-in with device_out -> Dirichlet reduction on the device -> only the reduced residual F_b
@@ -313,43 +355,52 @@ def run_b200(args, rank, world, local_rank):
                 "api": "plug-in (device_out=True) + boundary.DeviceBoundaryCondition.ApplyDirichletGetReducedMatrices; K_b stays on the device"}
     del Kb
 
-    # ------------------------------------------------------------------ roofline of the dominant kernel
-    hbm_peak, peak_src = measured_peaks()
+    # ------------------------------------------------------------------ roofline
     nnode_per_elem = nnode / float(nelem_local)
     # B = 8 npe + (nnode/nelem)(2*8*d) + (nnode/nelem) 8 nvar + 4 ndof^2 + 8 nnz/nelem
     B_alg = 8 * 10 + nnode_per_elem * (2 * 8 * 3) + nnode_per_elem * 8 * 3 + 4 * ndof * ndof + 8.0 * nnz / nelem_local
     Fl_ref = 8 * (10 * 9 * 10 + 100 + 150 + (2 * 30 * 6 + 2 * 30)) + 8 * (2 * 36 * 30 + 2 * 6 * 900 + 2 * 900 + 25 * 100)
     dfma = backend.measure_fp64_peak(False, 20000)
     launches += 4
-    traffic = {}
+    traffic, traffic_src = {}, None
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
             traffic = json.load(open(tr))
+            traffic_src = traffic.get("_source")
         except Exception:
             traffic = {}
+    if not traffic_src:
+        traffic = {}          # only a capture that names its commit / command is quoted
     k_step = k_elem + k_csr + k_T
-    # per-kernel algorithmic bytes per element.  Element kernel: SURVEY.md 8(d)'s whole-path figure B (state in, K values out).
-    # CSR reduction: what it has to move in this design -- the K_e rows it sums (8 ndof^2), the uint16 rank map (2 npe^2) and the
-    # CSR values it writes (8 nnz/nelem).
+    step_ms = ms / args.steps
+    # what each kernel has to move in THIS design (not SURVEY's whole-path figure): the element kernel reads the state and writes
+    # the K_e scratch and the per-element tractions; the reduction reads the scratch and the uint16 rank map and writes the CSR values
+    B_elem = 8 * 10 / 2 + nnode_per_elem * 48 + 8.0 * ndof * ndof + 8.0 * ndof
     B_csr = 8.0 * ndof * ndof + 2.0 * 10 * 10 + 8.0 * nnz / nelem_local
-    kernels = {
-        "implicit_iso_warp_kernel<10,8>": {"ms": float(k_elem), "bytes_per_element": B_alg, "traffic_key": "implicit_iso_warp_kernel_bytes_per_launch"},
-        "csr_gather_kernel<3,10>": {"ms": float(k_csr), "bytes_per_element": B_csr, "traffic_key": "csr_gather_kernel_bytes_per_launch"},
-    }
-    dom = max(kernels, key=lambda k: kernels[k]["ms"])
-    def _roof(name):
-        kk = kernels[name]
-        ach = kk["bytes_per_element"] * nelem_local / (kk["ms"] * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get(kk["traffic_key"]),
-                "kernel": name, "kernel_ms": kk["ms"], "algorithmic_bytes_per_element": kk["bytes_per_element"],
-                "share_of_step": kk["ms"] / k_step}
-    roof = _roof(dom)
-    roof["peak_source"] = peak_src
-    roof["other_kernels"] = [_roof(k) for k in kernels if k != dom] + [{"kernel": "gather_nodes_kernel<3>", "kernel_ms": float(k_T)}]
-    # the whole step against the same roofline: SURVEY 8(d)'s compulsory bytes over all three kernels
-    roof["step"] = {"achieved": B_alg * nelem_local / (k_step * 1e-3) / 1e9, "frac": B_alg * nelem_local / (k_step * 1e-3) / 1e9 / hbm_peak,
-                    "ms": float(k_step), "algorithmic_bytes_per_element": B_alg}
+    kernels = [
+        {"kernel": "implicit_iso_warp_kernel<10,8>", "kernel_ms": float(k_elem), "design_bytes_per_element": B_elem,
+         "design_GBps": B_elem * nelem_local / (k_elem * 1e-3) / 1e9, "traffic": traffic.get("implicit_iso_warp_kernel_bytes_per_launch"),
+         "share_of_step": float(k_elem / k_step)},
+        {"kernel": "csr_gather_kernel<3,10>", "kernel_ms": float(k_csr), "design_bytes_per_element": B_csr,
+         "design_GBps": B_csr * nelem_local / (k_csr * 1e-3) / 1e9, "traffic": traffic.get("csr_gather_kernel_bytes_per_launch"),
+         "share_of_step": float(k_csr / k_step)},
+        {"kernel": "gather_nodes_kernel<3>", "kernel_ms": float(k_T), "traffic": traffic.get("gather_nodes_kernel_bytes_per_launch"),
+         "share_of_step": float(k_T / k_step)}]
+    for kk in kernels:
+        if "design_GBps" in kk:
+            kk["design_frac_of_hbm_peak"] = kk["design_GBps"] / hbm_peak
+    tsum = [kk["traffic"] for kk in kernels]
+    ach = B_alg * nelem_local / (step_ms * 1e-3) / 1e9
+    dom = max(kernels, key=lambda kk: kk["kernel_ms"])
+    roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": float(sum(tsum)) if all(t is not None for t in tsum) else None, "traffic_source": traffic_src,
+            "scope": "whole step: SURVEY.md 8(d) algorithmic bytes per element x elements / device-timed ms_per_step (all kernels of one assembly)",
+            "algorithmic_bytes_per_element": B_alg, "algorithmic_bytes_per_step": B_alg * nelem_local, "step_ms": step_ms,
+            "kernel": dom["kernel"], "kernel_ms": dom["kernel_ms"],
+            "dominant_kernel_frac": B_alg * nelem_local / (dom["kernel_ms"] * 1e-3) / 1e9 / hbm_peak,
+            "dominant_kernel_note": "the same algorithmic bytes charged to the dominant kernel alone",
+            "peak_source": peak_src, "kernels": kernels}
     # executed fp64 work of the element kernel (LinearElastic takes the isotropic constant-tangent path):
     # kinematics 8 gp x (18 npe + ~120) + spatial gradients 8*10*9 + S_ab 8 gp x 100 node pairs x 9 (the warp-autonomous kernel
     # computes every block, no symmetry) + traction, FMA = 2; + the combination lamb S + mu S^T + mu tr I (~30 per node pair)
@@ -359,17 +410,23 @@ def run_b200(args, rank, world, local_rank):
               "kernel": "implicit_iso_warp_kernel<10,8>", "kernel_ms": float(k_elem),
               "reference_count": {"flops_per_element": Fl_ref, "equivalent_tflops": Fl_ref * nelem_local / (k_elem * 1e-3) / 1e12,
                                   "note": "what the reference's dense dgemm formulation would need for the same result (SURVEY.md 8d)"},
-              "peak_source": "measured in this run (fl_measure_fp64_peak, register-resident DFMA loop)"}
+              "peak_source": "builder-measured in this run (fl_measure_fp64_peak, register-resident DFMA loop); MEASURED_PEAKS.json has no fp64 entry"}
+    cfg = {"workload": "tet10 LinearElastic implicit K(CSR)+T, %d^3 hexes x6 = %d elements per GPU" % (n, nelem_owned),
+           "nelem_per_gpu": nelem_owned, "halo_elements": nelem_local - nelem_owned, "nnode_per_gpu": nnode, "nnz_per_gpu": nnz,
+           "mode": "CSR (recompute_sparsity_pattern=False), requires_geometry_update=1", "parallelism": "element slabs x%d" % world,
+           "l2": "inputs+scratch (%.1f GB per step) larger than L2, no flush needed" % ((nelem_local * 900 * 8 * 2 + nnz * 8) / 1e9)}
+    if row_info:
+        cfg.update(row_info)
     line = {"metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "tet10 LinearElastic implicit K(CSR)+T, %d^3 hexes x6 = %d elements per GPU" % (n, nelem_owned),
-                       "nelem_per_gpu": nelem_owned, "halo_elements": nelem_local - nelem_owned, "nnode_per_gpu": nnode, "nnz_per_gpu": nnz,
-                       "mode": "CSR (recompute_sparsity_pattern=False), requires_geometry_update=1", "parallelism": "element slabs x%d" % world,
-                       "l2": "inputs+scratch (%.1f GB per step) larger than L2, no flush needed" % ((nelem_local * 900 * 8 * 2 + nnz * 8) / 1e9)},
-            "clocks": clk,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "florence_b200.assembly._LowLevelAssemblyDF__LinearElastic_ (host numpy in, host numpy out)"},
+                    "api": "florence_b200.assembly._LowLevelAssemblyDF__LinearElastic_ (host numpy in, host numpy out)",
+                    "host_results": "views of the 2-deep pinned result ring (opt-in assembly.reuse_host_buffers(True): valid until the "
+                                    "next-but-one call, what a Newton loop needs)",
+                    "fresh_arrays_value": nelem_owned * world * e2e_steps / fresh_s,
+                    "fresh_arrays_note": "default mode: every call returns newly allocated numpy arrays like the reference "
+                                         "(chunked D2H pipelined with a multi-threaded copy-out)"},
             "e2e_device_resident": resident,
             "roofline": roof, "roofline_fp64": roof64}
 
@@ -387,64 +444,113 @@ def run_b200(args, rank, world, local_rank):
     del V, T, Vh, Th
     h.close()
     assembly._handle_cache.clear()
+    assembly._pinned.clear()
     torch.cuda.empty_cache()
 
-    # ------------------------------------------------------------------ explicit hex27 NeoHookean line (config 3 shape, per-GPU slab)
-    if not args.no_explicit:
-        ne = args.explicit_n
-        part = partition.slab_partition_hex(ne, ne, ne, 2, rank, world, device=dev)
+    # ------------------------------------------------------------------ explicit central-difference lines (configs 3 and 5)
+    def explicit_line(p, matnum, matname, prm, rho, nxy, nz_local, nsteps, scaling, label):
+        """One explicit line: order-p hexahedra, nxy x nxy x nz_local elements on this rank, slabs stacked along z."""
+        part = partition.slab_partition_hex(nxy, nxy, nz_local, p, rank, world, device=dev,
+                                            lengths_per_rank=(1.0, 1.0, float(nz_local) / nxy))
         if world > 1:
             part.interface_first()      # interface elements first: their forces are exchanged while the interior ones are evaluated
-        Bs, Jh, AGh = flmesh.tables("hex", 2)
+        Bs, Jh, AGh = flmesh.tables("hex", p)
         hh = backend.AssemblyHandle(part.points, part.elements, Jh, AGh, Bs, device=dev)
-        mu, lamb, rho = 4.0e5, 2.0e6, 1100.0
-        mat_n = backend.make_material(1, rho, mu=mu, lamb=lamb)
-        ex = None
-        if world > 1:
-            ex = partition.InterfaceExchange(part, 3, dev, handle=hh)
-        integ = time_integrator.ExplicitStructuralDynamicIntegrator(hh, mat_n, rho=rho, exchange=ex)
-        hx = 1.0 / ne
-        dt_x = 0.2 * hx / np.sqrt((lamb + 2 * mu) / rho)
+        mat_n = backend.make_material(matnum, rho, **prm)
+        ex = partition.InterfaceExchange(part, 3, dev, handle=hh) if world > 1 else None
+        hx = 1.0 / nxy
+        lam_eff = prm["lamb"] + 2 * (prm.get("mu", 0.0) + prm.get("mu1", 0.0) + prm.get("mu2", 0.0))
+        dt_x = 0.2 * (hx / p) / np.sqrt(lam_eff / rho)
         nn = part.points.shape[0]
         fixed = torch.zeros(nn * 3, dtype=torch.uint8, device=dev)
-        x0 = flmesh.perturbed_state(part.points, hx / 2, 0.02, seed=7)  # node spacing is h/2 at p=2
-        if ex is not None:
-            # interface nodes must start from the same perturbed position on both owners
-            x0 = part.points + 0.02 * (hx / 2) * torch.sin(1000.0 * part.points)
-        integ.initialise(part.points, None, fixed, dt_x)
-        integ.Eulerx.copy_(x0.reshape(-1)); integ.internal_force(integ.Eulerx.view(nn, 3), out=integ.T)
-        integ.step(3, 2)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        integ.step(args.explicit_steps, 5)
-        a1.record()
-        torch.cuda.synchronize()
-        ems = max_over_ranks(a0.elapsed_time(a1))
-        launches += 2 * (args.explicit_steps + 3) + 4
-        ndof_global = 3 * (2 * ne + 1) * (2 * ne + 1) * (2 * ne * world + 1)
+        # a smooth perturbation that is a function of the position: interface nodes start identically on both owners
+        x0 = part.points + 0.02 * (hx / p) * torch.sin(1000.0 * part.points)
+
+        def make(exch, overlap=True):
+            integ = time_integrator.ExplicitStructuralDynamicIntegrator(hh, mat_n, rho=rho, exchange=exch, overlap=overlap)
+            integ.initialise(part.points, None, fixed, dt_x)
+            integ.Eulerx.copy_(x0.reshape(-1)); integ.internal_force(integ.Eulerx.view(nn, 3), out=integ.T)
+            integ.step(3, 2)
+            return integ
+
+        def timed(integ):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            st = integ.step(nsteps, 5)
+            a1.record()
+            torch.cuda.synchronize()
+            return max_over_ranks(a0.elapsed_time(a1)), st
+        integ = make(ex)
+        ems, st = timed(integ)
+        out = {}
+        if world > 1:
+            # the same local work without any exchange (interface nodes then miss the neighbours' forces: timing only) and with the
+            # exchange but no overlap: what the interface exchange costs per step, and what the overlap hides
+            ems_plain, _ = timed(make(ex, overlap=False))
+            ems_none, _ = timed(make(None))
+            out["exchange"] = {"ms_per_step_overlapped": ems / nsteps, "ms_per_step_not_overlapped": ems_plain / nsteps,
+                               "ms_per_step_no_exchange": ems_none / nsteps, "exchange_cost_ms_per_step": (ems - ems_none) / nsteps,
+                               "interface_bytes_per_step": ex.bytes_per_exchange(), "interface_elements": int(part.n_interface_elements or 0)}
+        NX = p * nxy + 1
+        nz_total = nz_local * world
+        ndof_global = 3 * NX * NX * (p * nz_total + 1)
         hh.set_timing(True)
         hh.assemble_explicit(integ.Eulerx.view(nn, 3), None, mat_n, 0)
         t_el, _, t_g = hh.get_timing()
         hh.set_timing(False)
-        nel = ne ** 3
-        B_x = 8 * 27 + (nn / nel) * (2 * 8 * 3) + (nn / nel) * 8 * 3
-        Fl_x = 27 * (10 * 9 * 27 + 100 + 500 + (2 * 81 * 6 + 2 * 81))
-        # executed: two DMMA GEMMs per batch of 8 elements (462 + 252 tiles of 256 FMAs, incl. tile padding) + ~350 fp64 ops per Gauss point
-        Fl_x_exec = (462 + 252) / 8.0 * 512.0 + 27 * 350.0
-        line["explicit"] = {"metric": "explicit DOF-updates/s", "value": ndof_global * args.explicit_steps / (ems * 1e-3), "unit": "DOF-updates/s",
-                            "elements_per_s": nel * world * args.explicit_steps / (ems * 1e-3), "ms_per_step": ems / args.explicit_steps,
-                            "steps": args.explicit_steps, "blew_up": bool(integ.blew_up()),
-                            "config": {"workload": "hex27 NeoHookean explicit central difference, %d^3 elements per GPU" % ne, "ndof": ndof_global,
-                                       "interface_bytes_per_step": 0 if ex is None else ex.bytes_per_exchange()},
-                            "roofline": {"bound": "hbm", "achieved": B_x * nel / (t_el * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                         "frac": B_x * nel / (t_el * 1e-3) / 1e9 / hbm_peak, "kernel": "explicit_elements_mma_kernel<NeoHookean,27,27,8>",
-                                         "kernel_ms": t_el, "gather_ms": t_g},
-                            "roofline_fp64": {"achieved": Fl_x_exec * nel / (t_el * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
-                                              "frac": Fl_x_exec * nel / (t_el * 1e-3) / 1e12 / dfma, "flops_per_element_executed": Fl_x_exec,
-                                              "reference_count": {"flops_per_element": Fl_x,
-                                                                  "equivalent_tflops": Fl_x * nel / (t_el * 1e-3) / 1e12}}}
+        nel = nxy * nxy * nz_local
+        npe = (p + 1) ** 3
+        ng = npe
+        B_x = 8 * npe + (nn / nel) * (2 * 8 * 3) + (nn / nel) * 8 * 3
+        matfl = 350.0 if matnum == 1 else 450.0
+        Fl_x = ng * (10 * 9 * npe + 100 + 500 + (2 * 3 * npe * 6 + 2 * 3 * npe))
+        # useful work of the regrouped algebra: Jacobian GEMM (3 ng x npe x 6) + traction GEMM (npe x 3 ng x 3), FMA = 2, + the
+        # kinematics / material law per Gauss point; "executed" adds the padding of the 8x8x4 DMMA tiles (NE elements per batch)
+        Fl_useful = 2.0 * (3 * ng) * npe * 6 + 2.0 * npe * (3 * ng) * 3 + ng * matfl
+        NE = 8 if p == 2 else 32
+        t1 = ((3 * ng + 7) // 8) * ((npe + 3) // 4) * (6 * NE // 8)
+        t3 = ((npe + 7) // 8) * ((3 * ng + 3) // 4) * (3 * NE // 8)
+        Fl_exec = (t1 + t3) / float(NE) * 512.0 + ng * matfl
+        kname = "explicit_elements_mma_kernel<%s,%d,%d,%d>" % (matname, npe, ng, NE)
+        out.update({"metric": "explicit DOF-updates/s", "value": ndof_global * nsteps / (ems * 1e-3), "unit": "DOF-updates/s",
+                    "elements_per_s": nel * world * nsteps / (ems * 1e-3), "ms_per_step": ems / nsteps, "steps": nsteps,
+                    "scaling": scaling, "status": int(st), "blew_up": bool(st),
+                    "config": {"workload": label, "ndof": ndof_global, "elements_per_gpu": nel,
+                               "interface_bytes_per_step": 0 if ex is None else ex.bytes_per_exchange()},
+                    "roofline": {"bound": "hbm", "achieved": B_x * nel / (t_el * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": B_x * nel / (t_el * 1e-3) / 1e9 / hbm_peak, "kernel": kname, "kernel_ms": t_el, "gather_ms": t_g,
+                                 "note": "fp64-pipe bound (SURVEY.md 8d): see roofline_fp64"},
+                    "roofline_fp64": {"achieved": Fl_useful * nel / (t_el * 1e-3) / 1e12, "peak": dfma, "unit": "TFLOP/s",
+                                      "frac": Fl_useful * nel / (t_el * 1e-3) / 1e12 / dfma, "flops_per_element_useful": Fl_useful,
+                                      "flops_per_element_executed_incl_tile_padding": Fl_exec,
+                                      "frac_executed": Fl_exec * nel / (t_el * 1e-3) / 1e12 / dfma,
+                                      "peak_source": "builder-measured in this run (fl_measure_fp64_peak)",
+                                      "reference_count": {"flops_per_element": Fl_x, "equivalent_tflops": Fl_x * nel / (t_el * 1e-3) / 1e12}}})
         hh.close()
+        torch.cuda.empty_cache()
+        return out, (2 * (nsteps + 3) + 4) * (3 if world > 1 else 1)
+
+    if not args.no_explicit:
+        ne = args.explicit_n
+        line["explicit"], k = explicit_line(2, 1, "NeoHookean", dict(mu=4.0e5, lamb=2.0e6), 1100.0, ne, ne, args.explicit_steps, "weak",
+                                            "config 3 shape: hex27 NeoHookean explicit central difference, %d^3 elements per GPU" % ne)
+        launches += k
+        if world > 1 and ne % world == 0:
+            line["explicit3_strong"], k = explicit_line(2, 1, "NeoHookean", dict(mu=4.0e5, lamb=2.0e6), 1100.0, ne, ne // world,
+                                                        args.explicit_steps, "strong",
+                                                        "config 3: hex27 NeoHookean, %d^3 elements in total, %d z-layers per GPU" % (ne, ne // world))
+            launches += k
+    if not args.no_explicit and not args.no_config5:
+        ne = args.explicit_n
+        mu5, nu5 = 1.0e6, 0.495        # car_crash_analysis constants (SURVEY.md 8d config 5)
+        prm5 = dict(mu1=mu5, mu2=0.0, lamb=2.0 * mu5 * nu5 / (1.0 - 2.0 * nu5))
+        line["explicit5a"], k = explicit_line(1, 2, "MooneyRivlin", prm5, 8000.0, ne, ne, args.explicit_steps, "weak",
+                                              "config 5a: hex8 MooneyRivlin explicit, %d^3 elements per GPU stacked in z" % ne)
+        launches += k
+        line["explicit5b"], k = explicit_line(2, 2, "MooneyRivlin", prm5, 8000.0, ne, ne, args.explicit_steps, "weak",
+                                              "config 5b: hex27 MooneyRivlin explicit, %d^3 elements per GPU stacked in z" % ne)
+        launches += k
     # ------------------------------------------------------------------ config 4: EM_108 p=3 hex Newton-step assembly (DMMA local K)
     if not args.no_hiorder:
         n4 = args.hiorder_n
@@ -485,12 +591,53 @@ def run_b200(args, rank, world, local_rank):
                            "config": {"workload": "hex64 (p=3) IsotropicElectroMechanics_108 Newton-step K(CSR)+T, %d^3 elements per GPU" % n4,
                                       "ndof_per_element": 256, "nnz_per_gpu": nnz4},
                            "roofline": {"bound": "tensor", "achieved": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
-                                        "frac": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12 / dmma, "kernel": "implicit_elements_mma_kernel<EM_108,64,64,6>",
+                                        "frac": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12 / dmma,
+                                        "frac_whole_step": fl_exec * nel4 / (hms * 1e-3) / 1e12 / dmma,
+                                        "kernel": "implicit_elements_mma_kernel<EM_108,64,64,6>",
                                         "kernel_ms": t4[0], "csr_gather_wide_ms": t4[1],
-                                        "peak_source": "measured in this run (fl_measure_fp64_peak, mma.sync.m8n8k4.f64 loop)",
+                                        "peak_source": "builder-measured in this run (fl_measure_fp64_peak, mma.sync.m8n8k4.f64 loop); "
+                                                       "MEASURED_PEAKS.json has no fp64 entry",
                                         "flops_per_element_executed_on_tensor_cores": fl_exec}}
         del V4, T4
         h4.close()
+        torch.cuda.empty_cache()
+    # ------------------------------------------------------------------ config 1: Poisson, p = 4 hexahedra (hex125)
+    if not args.no_poisson:
+        B1, J1, A1 = flmesh.tables("hex", 4)
+        pois = {}
+        for n1 in (6, 16):
+            p1, e1_ = flmesh.box_hex_mesh(n1, n1, n1, p=4, device=dev)
+            h1 = backend.AssemblyHandle(p1, e1_, J1, A1, B1, device=dev)
+            nnz1 = h1.build_pattern(1)
+            etens = -2.35 * np.eye(3)
+            for _ in range(3):
+                h1.assemble_laplacian(etens, True, mode="csr")
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nrep = 5
+            c0.record()
+            for _ in range(nrep):
+                h1.assemble_laplacian(etens, True, mode="csr")
+            c1.record()
+            torch.cuda.synchronize()
+            pms = max_over_ranks(c0.elapsed_time(c1)) / nrep
+            h1.set_timing(True)
+            h1.assemble_laplacian(etens, True, mode="csr")
+            tk = h1.get_timing()
+            h1.set_timing(False)
+            launches += 2 * (nrep + 4)
+            nel1 = e1_.shape[0]
+            # upper triangle, npe^2/2 * ng * 6 flops = 5.9 Mflop per hex125 element
+            fl1 = 125 * 125 / 2.0 * 125 * 6
+            pois["%d^3" % n1] = {"elements": nel1, "nnz": nnz1, "ms_per_assembly": pms, "elements_per_s": nel1 * world / (pms * 1e-3),
+                                 "element_kernel_ms": tk[0], "csr_reduction_ms": tk[1],
+                                 "fp64_TFLOPs_reference_count": fl1 * nel1 / (tk[0] * 1e-3) / 1e12,
+                                 "fp64_frac_reference_count": fl1 * nel1 / (tk[0] * 1e-3) / 1e12 / dfma}
+            h1.close()
+        line["poisson"] = {"metric": "elements assembled/s (K, fp64)", "config": {"workload": "config 1: Poisson, hex125 (p=4), K(CSR); "
+                           "6^3 is the reference's simple_laplace mesh, 16^3 the same element at a size that fills the GPU"},
+                           "value": pois["6^3"]["elements_per_s"], "unit": "elements/s", "sizes": pois,
+                           "peak_source": "builder-measured DFMA peak of this run"}
         torch.cuda.empty_cache()
     line["gpu_launches"] = int(launches)
     if rank == 0:

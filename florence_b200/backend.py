@@ -323,23 +323,37 @@ class AssemblyHandle(object):
     # ---------------------------------------------------------------------------------------------- owned CSR row block
     def row_block(self, nvar, V, owned_nodes, node_map):
         """(indptr_block int64 [n_owned*nvar+1], cols_global int64, vals): the CSR rows of `owned_nodes` (ascending local ids) of the
-        locally assembled V with GLOBAL column dof numbers, produced on the device (fl_row_block_build / fl_row_block_emit)."""
+        locally assembled V with GLOBAL column dof numbers, produced on the device (fl_row_block_build / fl_row_block_emit).
+        indptr_block and cols_global belong to the sparsity pattern and are built once per (nvar, owned set); every call emits the
+        values -- as a zero-copy slice of V when the owned nodes are a contiguous range (slab partitions), else compacted."""
         own = to_device(owned_nodes, torch.int32, self.device).reshape(-1)
-        nmap = to_device(node_map, torch.int64, self.device).reshape(-1)
         key = ("rowblock", nvar, own.data_ptr(), own.numel())
         cache = getattr(self, "_row_block_cache", None)
         if cache is None or cache[0] != key:
+            nmap = to_device(node_map, torch.int64, self.device).reshape(-1)
             indptr = torch.empty(own.numel() * nvar + 1, dtype=torch.int64, device=self.device)
             nnz = C.c_int64(0)
             with torch.cuda.device(self.device):
                 check(self.lib.fl_row_block_build(self._h, nvar, _ptr(own), own.numel(), _ptr(indptr), C.byref(nnz), _stream()))
-            self._row_block_cache = cache = (key, indptr, int(nnz.value), own)
-        _, indptr, nnz, own = cache
-        cols = torch.empty(nnz, dtype=torch.int64, device=self.device)
+                cols = torch.empty(int(nnz.value), dtype=torch.int64, device=self.device)
+                check(self.lib.fl_row_block_emit(self._h, nvar, None, _ptr(own), own.numel(), _ptr(nmap), _ptr(indptr), _ptr(cols), None,
+                                                 _stream()))
+            contiguous = own.numel() > 0 and int(own[-1].item()) - int(own[0].item()) + 1 == own.numel()
+            first = int(own[0].item()) if contiguous else -1
+            self._row_block_cache = cache = (key, indptr, int(nnz.value), own, cols, first)
+        _, indptr, nnz, own, cols, first = cache
+        if first >= 0:
+            # rows of consecutive nodes are consecutive in V: the block is V[start : start + nnz]
+            if not hasattr(self, "_nbr_start"):
+                self._nbr_start = {}
+            if (nvar, first) not in self._nbr_start:
+                ind = self.sparsity_pattern(nvar)[1]
+                self._nbr_start[(nvar, first)] = int(ind[first * nvar].item())
+            s0 = self._nbr_start[(nvar, first)]
+            return indptr, cols, V[s0:s0 + nnz]
         vals = torch.empty(nnz, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            check(self.lib.fl_row_block_emit(self._h, nvar, _ptr(V), _ptr(own), own.numel(), _ptr(nmap), _ptr(indptr), _ptr(cols), _ptr(vals),
-                                             _stream()))
+            check(self.lib.fl_row_block_emit(self._h, nvar, _ptr(V), _ptr(own), own.numel(), None, _ptr(indptr), None, _ptr(vals), _stream()))
         return indptr, cols, vals
 
 

@@ -534,7 +534,8 @@ int fl_row_block_build(fl_handle* h, int nvar, const int32_t* owned_nodes, int64
 
 int fl_row_block_emit(fl_handle* h, int nvar, const double* V, const int32_t* owned_nodes, int64_t n_owned, const int64_t* node_map,
                       const int64_t* indptr_block, int64_t* cols_global, double* vals, void* stream) {
-    if (!h || nvar < 1 || nvar > 4 || !V || !node_map || !indptr_block || !cols_global || !vals || (n_owned > 0 && !owned_nodes)) {
+    if (!h || nvar < 1 || nvar > 4 || !indptr_block || (n_owned > 0 && !owned_nodes) || (vals && !V) || (cols_global && !node_map) ||
+        (!vals && !cols_global)) {
         set_error("bad argument");
         return FL_ERR_INVALID;
     }

@@ -598,8 +598,8 @@ __global__ void row_block_emit_kernel(const int64_t* __restrict__ nbr_ptr, const
     for (int64_t t = lane; t < nvar * w; t += 32) {
         const int64_t c = t % w;
         const int64_t q = c / nvar;
-        vals[dst + t] = V[src + t];
-        cols[dst + t] = node_map[nbr_idx[p0 + q]] * nvar + (c - q * nvar);
+        if (vals) vals[dst + t] = V[src + t];
+        if (cols) cols[dst + t] = node_map[nbr_idx[p0 + q]] * nvar + (c - q * nvar);
     }
 }
 

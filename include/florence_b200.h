@@ -209,7 +209,9 @@ int fl_explicit_check(fl_handle *h, int64_t *growth_keys_dev, int64_t increment,
 /* Implicit multi-GPU: "each rank emits the CSR row block it owns" (the reference sums per-partition triplets on
  * the parent, Assembly.py:1000-1041).  owned_nodes: ascending local node ids owned by this rank; node_map: global node id of every
  * local node.  fl_row_block_build writes the int64 row pointer of the block (n_owned*nvar+1 entries, starting at 0) and returns
- * its nnz; fl_row_block_emit copies the owned rows of V (aligned with fl_pattern_export) and writes GLOBAL column dof numbers. */
+ * its nnz; fl_row_block_emit copies the owned rows of V (aligned with fl_pattern_export) into vals and writes GLOBAL column dof
+ * numbers into cols_global.  Either output may be NULL: the columns belong to the pattern and are emitted once, the values on
+ * every assembly. */
 int fl_row_block_build(fl_handle *h, int nvar, const int32_t *owned_nodes, int64_t n_owned, int64_t *indptr_block,
                        int64_t *nnz_block_host, void *stream);
 int fl_row_block_emit(fl_handle *h, int nvar, const double *V, const int32_t *owned_nodes, int64_t n_owned, const int64_t *node_map,

@@ -6,6 +6,10 @@ import collections, csv, io, json, os, subprocess, sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
+try:
+    COMMIT = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=HERE).stdout.strip()
+except Exception:
+    COMMIT = "unknown"
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
            "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -60,7 +64,10 @@ for rep in reps:
         name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "")
         out += ["## `%s`  (%s)" % (name, os.path.basename(rep)), "", "| metric | value | unit |", "|---|---|---|"]
         vals = {}
-        for m in METRICS:
+        # fp64 / tensor pipe counters: every column ncu collected for them (instruction counts by pipe and pipe-active cycles), so
+        # that tensor-pipe utilisation is a counter and not arithmetic
+        pipe = [c for c in h if ("dmma" in c or "pipe_fp64" in c or "pipe_tensor" in c) and c not in METRICS]
+        for m in METRICS + pipe:
             if m in h:
                 vals[m] = r[h.index(m)]
                 out.append("| %s | %s | %s |" % (m, r[h.index(m)], units[h.index(m)]))
@@ -75,6 +82,8 @@ for rep in reps:
             traffic.setdefault(key, rd + wr)
         except Exception:
             pass
+traffic["_source"] = "profiles/%s_summary.md: ncu --set full --clock-control none captures (%s) at commit %s; per launch, cold cache" % (
+    tag, ", ".join(os.path.basename(r) for r in reps), COMMIT)
 json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 open(os.path.join(HERE, "%s_summary.md" % tag), "w").write("\n".join(out) + "\n")
 print("\n".join(out[:40]))
