@@ -147,7 +147,8 @@ def _fresh_from_device(t):
         _stage[key] = [torch.empty(per, dtype=t.dtype, pin_memory=True) for _ in range(2)]
     bufs = _stage[key]
     if _pool is None:
-        _pool = ThreadPoolExecutor(4)
+        import os
+        _pool = ThreadPoolExecutor(max(2, min(8, len(os.sched_getaffinity(0)) // 2)))
     stream = torch.cuda.current_stream()
     pending = [None, None]          # per staging buffer: futures of the host copies still reading it
     events = [None, None]
@@ -155,7 +156,7 @@ def _fresh_from_device(t):
     def drain(k, lo, hi):
         events[k].synchronize()
         src = bufs[k].numpy()[:hi - lo]
-        parts = 4
+        parts = _pool._max_workers
         step = (hi - lo + parts - 1) // parts
         pending[k] = [_pool.submit(np.copyto, out[lo + q * step:min(lo + (q + 1) * step, hi)], src[q * step:min((q + 1) * step, hi - lo)])
                       for q in range(parts) if q * step < hi - lo]

@@ -194,7 +194,7 @@ int fl_destroy(fl_handle* h) {
     cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank); cudaFree(h->pat.rank_adj);
     dirichlet_free(h);
     cudaFree(h->contact.surf);
-    cudaFree(h->te); cudaFree(h->ke); cudaFree(h->flag); cudaFree(h->growth);
+    cudaFree(h->te); cudaFree(h->ke); cudaFree(h->ch); cudaFree(h->flag); cudaFree(h->growth);
     delete h;
     return FL_OK;
 }

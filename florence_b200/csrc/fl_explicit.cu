@@ -276,14 +276,25 @@ __global__ void explicit_update_kernel(const int64_t* __restrict__ adj_ptr, cons
         if (bad) atomicOr(nan_flag, 1);
     }
     if (growth) {
+        // block maximum first, and the global word is only touched when it would change: two same-address atomics per warp
+        // (4 M of them at 64 M nodes) serialise in L2 and cost more than the update itself
+        __shared__ double s_u[8], s_u0[8];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
             u0max = fmax(u0max, __shfl_xor_sync(0xffffffffu, u0max, o));
         }
-        if ((threadIdx.x & 31) == 0 && umax > -INFINITY) {
-            atomicMax(growth, ordered_key(umax));
-            atomicMax(growth + 1, ordered_key(u0max));
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { s_u[w] = umax; s_u0[w] = u0max; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nw = (blockDim.x + 31) >> 5;
+            for (int k = 1; k < nw; ++k) { umax = fmax(umax, s_u[k]); u0max = fmax(u0max, s_u0[k]); }
+            if (umax > -INFINITY) {
+                const long long ku = ordered_key(umax), k0 = ordered_key(u0max);
+                if (ku > *reinterpret_cast<volatile long long*>(growth)) atomicMax(growth, ku);
+                if (k0 > *reinterpret_cast<volatile long long*>(growth + 1)) atomicMax(growth + 1, k0);
+            }
         }
     }
 }

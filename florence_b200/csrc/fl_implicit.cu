@@ -189,6 +189,9 @@ laplacian_elements_kernel(const int32_t* __restrict__ conn, const double* __rest
 
 int launch_laplacian_elements(fl_handle* h, const double* e_dev, int symmetric, double* ke, cudaStream_t st) {
     const int npe = h->npe, ng = h->ng, ldg = h->ldg, D = h->ndim;
+    // p >= 3 hexahedra: K = JmT (Q_g Jm) is the shared-operand GEMM of the mechanics kernels with nvar = 1 -> fp64 tensor cores
+    if (D == 3 && h->use_mma_implicit && npe == 125 && ng == 125) return launch_laplacian_mma<125, 125, 12, 4>(h, e_dev, symmetric, ke, st);
+    if (D == 3 && h->use_mma_implicit && npe == 64 && ng == 64) return launch_laplacian_mma<64, 64, 12, 0>(h, e_dev, symmetric, ke, st);
     constexpr int A = 8;
     const int xstride = (npe * D) | 1;
     const size_t jm_bytes = sizeof(double) * D * npe * ldg;

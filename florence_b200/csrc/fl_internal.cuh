@@ -86,6 +86,7 @@ struct fl_handle {
     // scratch (grown on demand)
     double* te = nullptr;  size_t te_bytes = 0;   // per-element traction buffer nelem*ndof
     double* ke = nullptr;  size_t ke_bytes = 0;   // per-element stiffness buffer nelem*ndof^2 (CSR mode)
+    double* ch = nullptr;  size_t ch_bytes = 0;   // per-element Chat_g blocks between the prologue and the DMMA kernel (p >= 2 hexahedra)
     int32_t* flag = nullptr;                       // device status: [0] bit 0 NaN, bit 1 growth blow-up; [1] increment of first detection
     int64_t* growth = nullptr;                     // running maxima (ordered keys) of U and U0 for the blow-up test
     int64_t el0 = 0, el1 = -1;                     // element range of the explicit force call in flight (el1 < 0: all)
