@@ -13,7 +13,19 @@ h = backend.AssemblyHandle(pts, els, Jm, AG, B, device=dev)
 mu = 5e4; lamb = 2 * mu * 0.4 / (1 - 0.8)
 mat = backend.make_material(8, 1200.0, mu1=mu, mu2=mu, lamb=lamb, eps_2=4 * 8.8541e-12)
 h.build_pattern(4)
-for _ in range(3):
+for _ in range(1):
     V, T = h.assemble_implicit(x, phi, mat, 1, True, mode="csr")
 torch.cuda.synchronize()
-print("done")
+print("done hex64")
+h.close()
+# config 1's element: Poisson on hex125 (DMMA GEMM kernel with nvar = 1)
+import numpy as np
+n1 = max(4, n // 2)
+pts, els = flmesh.box_hex_mesh(n1, n1, n1, p=4, device=dev)
+B, Jm, AG = flmesh.tables("hex", 4)
+h = backend.AssemblyHandle(pts, els, Jm, AG, B, device=dev)
+h.build_pattern(1)
+for _ in range(2):
+    V = h.assemble_laplacian(-2.35 * np.eye(3), True, mode="csr")
+torch.cuda.synchronize()
+print("done laplacian")

@@ -60,13 +60,18 @@ for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     h, units = rr[0], rr[1]
+    seen = set()
     for r in rr[2:]:
         name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "")
+        if name in seen:          # the drivers repeat every assembly a few times: one capture per kernel is summarised
+            continue
+        seen.add(name)
         out += ["## `%s`  (%s)" % (name, os.path.basename(rep)), "", "| metric | value | unit |", "|---|---|---|"]
         vals = {}
         # fp64 / tensor pipe counters: every column ncu collected for them (instruction counts by pipe and pipe-active cycles), so
         # that tensor-pipe utilisation is a counter and not arithmetic
-        pipe = [c for c in h if ("dmma" in c or "pipe_fp64" in c or "pipe_tensor" in c) and c not in METRICS]
+        pipe = [c for c in h if ("dmma" in c or "pipe_fp64" in c or "pipe_tensor" in c) and c not in METRICS
+                and c.endswith("avg.pct_of_peak_sustained_active") and "hmma" not in c and "imma" not in c]
         for m in METRICS + pipe:
             if m in h:
                 vals[m] = r[h.index(m)]
