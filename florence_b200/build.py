@@ -19,9 +19,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 # (object name, source, extra defines)
 UNITS = [("fl_api", "fl_api.cu", []), ("fl_explicit", "fl_explicit.cu", []), ("fl_pattern", "fl_pattern.cu", []),
-         ("fl_dirichlet", "fl_dirichlet.cu", [])] + \
+         ("fl_dirichlet", "fl_dirichlet.cu", []), ("fl_gather", "fl_gather.cu", []), ("fl_stream", "fl_stream.cu", [])] + \
         [("fl_implicit_%d" % k, "fl_implicit.cu", ["-DFL_IMPL_PART=%d" % k]) for k in range(7)]
-HEADERS = ["fl_math.cuh", "fl_internal.cuh", "fl_implicit.cuh", "fl_explicit_mma.cuh", "fl_implicit_mma.cuh", "fl_implicit_warp.cuh", os.path.join("..", "..", "include", "florence_b200.h")]
+HEADERS = ["fl_math.cuh", "fl_internal.cuh", "fl_implicit.cuh", "fl_explicit_mma.cuh", "fl_implicit_mma.cuh", "fl_implicit_warp.cuh", "fl_gather.cuh", os.path.join("..", "..", "include", "florence_b200.h")]
 
 
 def _newest_header():

@@ -168,6 +168,8 @@ int fl_set_option(fl_handle* h, int option, int value) {
     if (option == 0) { h->use_mma = value ? 1 : 0; return FL_OK; }
     if (option == 1) { h->use_mma_implicit = value; return FL_OK; }
     if (option == 2) { h->use_warp_iso = value; return FL_OK; }
+    if (option == 3) { h->use_reg_gather = value ? 1 : 0; return FL_OK; }
+    if (option == 4) { h->use_stream = value; return FL_OK; }
     set_error("unknown option %d", option);
     return FL_ERR_INVALID;
 }
@@ -193,6 +195,8 @@ int fl_destroy(fl_handle* h) {
     cudaFree(h->conn); cudaFree(h->points); cudaFree(h->jm); cudaFree(h->jmT); cudaFree(h->bases); cudaFree(h->gw);
     cudaFree(h->adj_ptr); cudaFree(h->adj_idx); cudaFree(h->pat.nbr_ptr); cudaFree(h->pat.nbr_idx); cudaFree(h->pat.rank); cudaFree(h->pat.rank_adj);
     dirichlet_free(h);
+    gather_plan_free(h);
+    stream_plan_free(h);
     cudaFree(h->contact.surf);
     cudaFree(h->te); cudaFree(h->ke); cudaFree(h->ch); cudaFree(h->flag); cudaFree(h->growth);
     delete h;
@@ -220,6 +224,11 @@ int fl_pattern_build(fl_handle* h, int nvar, int64_t* nnz_host) {
     if (!h || nvar < 1 || nvar > 4) { set_error("bad argument"); return FL_ERR_INVALID; }
     int rc = pattern_build(h);
     if (rc) return rc;
+    // the plan of the register-resident CSR reduction depends on the pattern and nvar only: built here, outside the assembly calls
+    if (h->use_reg_gather && reg_gather_supported(h, nvar)) {
+        rc = gather_plan_ensure(h, nvar);
+        if (rc) return rc;
+    }
     if (nnz_host) *nnz_host = h->pat.nnzb * nvar * nvar;
     return FL_OK;
 }
@@ -320,6 +329,12 @@ int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Euler
         rc = ensure_scratch(&h->ke, &h->ke_bytes, sizeof(double) * h->nelem * ndof * ndof);
         if (rc) return rc;
         ke = h->ke;
+    }
+    // CSR values of the isotropic constant-tangent material on tet10 / hex8: K_e stored along a space-filling curve, reduction in
+    // completion order (fl_stream.cu)
+    if (mode == FL_MODE_CSR && mat->material_number == MAT_LINEAR_ELASTIC && formulation_number == 0 && stream_csr_supported(h)) {
+        mark(h, 0, st);
+        return launch_stream_iso_csr(h, Eulerx, mat, requires_geometry_update ? 1 : 0, V, T, st);
     }
     // CSR mode with the DMMA kernel of p = 3 hexahedra: the K_e scratch is laid out as dof-pair planes (full-sector fragment stores);
     // the wide CSR reduction reads the same layout.  COO mode always keeps the reference's element-major triplet order.

@@ -60,11 +60,15 @@ struct iso_warp_shape {
                   "16-byte stores need 16-byte aligned rows");
 };
 
-template <int NPE, int NG>
+// STREAM: the kernel publishes its progress for a concurrently running CSR reduction (fl_stream.cu).  flags[group] = epoch is
+// stored with release semantics once every K_e row of the group has reached global memory (the bulk copies have completed, not
+// merely been read out of shared memory); the stores of a group are published after the kinematics phase of the warp's NEXT group,
+// when their completion costs no wait.
+template <int NPE, int NG, bool STREAM = false>
 __global__ void __launch_bounds__(IW_WARPS * 32, FL_IW_MINB)
 implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                          const double* __restrict__ jm_g, const double* __restrict__ gw_g, int64_t nelem, int ldg_g, int update,
-                         MatParams prm, double* __restrict__ ke, double* __restrict__ te) {
+                         MatParams prm, double* __restrict__ ke, double* __restrict__ te, int32_t* __restrict__ flags, int32_t epoch) {
     using S = iso_warp_shape<NPE, NG>;
     constexpr int D = 3, EPW = S::EPW, NDOF = S::NDOF, LPE = S::LPE;
     extern __shared__ __align__(16) double smem_w[];
@@ -103,9 +107,20 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
         }
         asm volatile("cp.async.commit_group;");
     };
+    // all K_e rows of group `g` are in global memory: publish
+    auto publish = [&](int64_t g) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(flags + g), "r"(epoch) : "memory");
+        }
+    };
     int64_t grp = (int64_t)blockIdx.x * IW_WARPS + warp;
     if (grp < ngroups) gather(grp, 0);
     int buf = 0;
+    int64_t prev = -1;
     for (; grp < ngroups; grp += wstride, buf ^= 1) {
         const int64_t e0 = grp * EPW;
         const int ne = (int)min((int64_t)EPW, nelem - e0);
@@ -175,6 +190,10 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
             }
         }
         __syncwarp();
+        if (STREAM) {
+            if (prev >= 0) publish(prev);
+            prev = grp;
+        }
         // ---- phase 3 / 4: lane = (element, node pair)
         {
             const int el = lane / LPE, t = lane - el * LPE;
@@ -275,6 +294,7 @@ implicit_iso_warp_kernel(const int32_t* __restrict__ conn, const double* __restr
         __syncwarp();
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (STREAM && prev >= 0) publish(prev);
 }
 
 template <int NPE, int NG>
@@ -289,7 +309,7 @@ int launch_impl_iso_warp(fl_handle* h, const double* Eulerx, const MatParams& pr
     const int64_t nblk = (ngroups + IW_WARPS - 1) / IW_WARPS;
     const int grid = (int)(nblk < (int64_t)occ * h->sm_count ? nblk : (int64_t)occ * h->sm_count);
     if (grid == 0) return FL_OK;
-    kern<<<grid, IW_WARPS * 32, S::SMEM, st>>>(h->conn, h->points, Eulerx, h->jm, h->gw, h->nelem, h->ldg, update, prm, ke, te);
+    kern<<<grid, IW_WARPS * 32, S::SMEM, st>>>(h->conn, h->points, Eulerx, h->jm, h->gw, h->nelem, h->ldg, update, prm, ke, te, nullptr, 0);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }

@@ -51,6 +51,38 @@ struct Contact {
     double L = 0, kappa = 0, tol = 0;
 };
 
+// Plan of the register-resident CSR value reduction (fl_gather.cuh): the neighbour list of every node cut into work items of up to 96 slots,
+// and per (item, visit) one packed record: flat connectivity index + slot -> local-node fields.  All pointers are device arrays.
+struct GatherItem {
+    int64_t rec_off;    // first record of the item, in 32-bit words from GatherPlan::recs
+    int64_t v_base;     // offset in V of row 0, first column of the item
+    int32_t nvis;       // visits (elements) of the node
+    int32_t w;          // row width nvar * neighbours
+    int32_t nslots;     // node slots (neighbour columns) of the item (<= 96)
+    int32_t ng;         // groups of 32 slots the item spans (1..3); its records have 2 + FWG*ng words
+};
+struct GatherPlan {
+    int nvar = 0, bits = 0;
+    int64_t nitems = 0, nwords = 0;
+    GatherItem* items = nullptr;    // nitems, node-major (streamed assembly: in completion order)
+    uint32_t* recs = nullptr;       // nwords: the records of all items, [item][visit][2 + FWG*ng words]
+};
+
+// Curve-ordered CSR assembly (fl_stream.cu): the element kernel walks the elements in space-filling-curve order; the CSR reduction
+// follows in completion order, optionally beside it on a second stream (then the element kernel publishes its progress).
+struct StreamPlan {
+    int npe = 0;
+    int64_t ngroups = 0;
+    int32_t* conn_p = nullptr;      // connectivity in storage (curve) order
+    int32_t* adj_idx_p = nullptr;   // adjacency (node -> visits, ascending ORIGINAL element number) as storage flat indices
+    GatherPlan gp;                  // records hold storage flat indices, items in completion order
+    int32_t* flags = nullptr;       // ngroups: epoch of the call whose K_e rows of the group are complete
+    int32_t* err = nullptr;         // set by a reduction warp that gave up waiting
+    int32_t epoch = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+
 template <int D>
 __device__ __forceinline__ bool contact_force(const Contact& c, const double* __restrict__ x, double* f) {
     double gap = 0.0;
@@ -86,6 +118,13 @@ struct fl_handle {
     // scratch (grown on demand)
     double* te = nullptr;  size_t te_bytes = 0;   // per-element traction buffer nelem*ndof
     double* ke = nullptr;  size_t ke_bytes = 0;   // per-element stiffness buffer nelem*ndof^2 (CSR mode)
+    fl::GatherPlan gplan;        // built on the first CSR reduction that can use it (fl_gather.cu)
+    fl::StreamPlan splan;
+    int use_stream = 1;          // LinearElastic tet10 (hex8 with option 2 = 2) in CSR mode (fl_stream.cu, fl_set_option 4): 1 = K_e along
+                                 // a space-filling curve, reduction in completion order; 2 = the same with both kernels running
+                                 // concurrently (measured slower); 3 = the kernels of 2 one after the other; 0 = off
+    int use_reg_gather = 0;      // CSR value reduction of the element-order paths: 1 = register-resident slot-owner gather
+                                 // (fl_gather.cuh), 0 = shared-memory row-buffer kernels of fl_pattern.cu (fl_set_option 3)
     double* ch = nullptr;  size_t ch_bytes = 0;   // per-element Chat_g blocks between the prologue and the DMMA kernel (p >= 2 hexahedra)
     int32_t* flag = nullptr;                       // device status: [0] bit 0 NaN, bit 1 growth blow-up; [1] increment of first detection
     int64_t* growth = nullptr;                     // running maxima (ordered keys) of U and U0 for the blow-up test
@@ -134,6 +173,19 @@ int launch_row_block_emit(fl_handle* h, int nvar, const double* V, const int32_t
                           const int64_t* indptr_block, int64_t* cols, double* vals, cudaStream_t st);
 int launch_sfc_order(const double* points, const int64_t* elements, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
                      cudaStream_t st);
+int launch_sfc_order_conn(const double* points, const int32_t* conn, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
+                          cudaStream_t st);
+// fl_gather.cu
+void gather_plan_free(fl_handle* h);
+void gather_plan_release(GatherPlan& g);
+int gather_plan_build(fl_handle* h, int nvar, const int32_t* flat_store, bool by_completion, GatherPlan* out);
+bool reg_gather_supported(const fl_handle* h, int nvar);
+int gather_plan_ensure(fl_handle* h, int nvar);
+int launch_csr_gather_reg(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st);
+// fl_stream.cu
+void stream_plan_free(fl_handle* h);
+bool stream_csr_supported(const fl_handle* h);
+int launch_stream_iso_csr(fl_handle* h, const double* Eulerx, const fl_material* mat, int update, double* V, double* T, cudaStream_t st);
 // fl_dirichlet.cu
 void dirichlet_free(fl_handle* h);
 int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_out);

@@ -557,6 +557,7 @@ static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaS
 
 int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st) {
     if (!h->pat.nbr_ptr) { set_error("fl_pattern_build has not been called"); return FL_ERR_STATE; }
+    if (h->use_reg_gather && reg_gather_supported(h, nvar)) return launch_csr_gather_reg(h, nvar, ke, V, st);
     switch (nvar) {
         case 1: return launch_csr_gather_NV<1>(h, ke, V, st);
         case 2: return launch_csr_gather_NV<2>(h, ke, V, st);
@@ -672,7 +673,8 @@ __device__ __forceinline__ uint64_t spread3(uint64_t x) {   // 21 bits -> every 
     return x;
 }
 
-__global__ void morton_keys_kernel(const double* __restrict__ pts, const int64_t* __restrict__ els, int64_t nelem, int npe, int D,
+template <typename IdxT>
+__global__ void morton_keys_kernel(const double* __restrict__ pts, const IdxT* __restrict__ els, int64_t nelem, int npe, int D,
                                    const long long* __restrict__ box, uint64_t* __restrict__ keys, int64_t* __restrict__ iota) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nelem) return;
@@ -693,8 +695,9 @@ __global__ void morton_keys_kernel(const double* __restrict__ pts, const int64_t
     iota[e] = e;
 }
 
-int launch_sfc_order(const double* points, const int64_t* elements, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
-                     cudaStream_t st) {
+template <typename IdxT>
+static int sfc_order_T(const double* points, const IdxT* elements, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
+                       cudaStream_t st) {
     if (nelem == 0) return FL_OK;
     DevBuf box, keys, keys_out, iota, tmp;
     FL_CUDA_CHECK(box.alloc(sizeof(long long) * 6));
@@ -706,8 +709,8 @@ int launch_sfc_order(const double* points, const int64_t* elements, int64_t nele
     FL_CUDA_CHECK(keys.alloc(sizeof(uint64_t) * nelem));
     FL_CUDA_CHECK(keys_out.alloc(sizeof(uint64_t) * nelem));
     FL_CUDA_CHECK(iota.alloc(sizeof(int64_t) * nelem));
-    morton_keys_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>(points, elements, nelem, npe, ndim, box.as<long long>(),
-                                                                        keys.as<uint64_t>(), iota.as<int64_t>());
+    morton_keys_kernel<IdxT><<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>(points, elements, nelem, npe, ndim, box.as<long long>(),
+                                                                              keys.as<uint64_t>(), iota.as<int64_t>());
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.as<uint64_t>(), keys_out.as<uint64_t>(), iota.as<int64_t>(), perm, nelem, 0, 63, st);
     FL_CUDA_CHECK(tmp.alloc(tb));
@@ -715,6 +718,16 @@ int launch_sfc_order(const double* points, const int64_t* elements, int64_t nele
     FL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.as<uint64_t>(), keys_out.as<uint64_t>(), iota.as<int64_t>(), perm, nelem, 0, 63, st));
     FL_CUDA_CHECK(cudaStreamSynchronize(st));
     return FL_OK;
+}
+
+int launch_sfc_order(const double* points, const int64_t* elements, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
+                     cudaStream_t st) {
+    return sfc_order_T<int64_t>(points, elements, nelem, npe, ndim, nnode, perm, st);
+}
+
+int launch_sfc_order_conn(const double* points, const int32_t* conn, int64_t nelem, int npe, int ndim, int64_t nnode, int64_t* perm,
+                          cudaStream_t st) {
+    return sfc_order_T<int32_t>(points, conn, nelem, npe, ndim, nnode, perm, st);
 }
 
 }  // namespace fl
