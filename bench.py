@@ -375,17 +375,18 @@ def run_b200(args, rank, world, local_rank):
     k_step = k_elem + k_csr + k_T
     step_ms = ms / args.steps
     # what each kernel has to move in THIS design (not SURVEY's whole-path figure): the element kernel reads the state and writes
-    # the K_e scratch and the per-element tractions; the reduction reads the scratch and the uint16 rank map and writes the CSR values
+    # the K_e scratch (along the Morton curve) and the per-element tractions; the reduction reads the scratch and its packed plan
+    # (per node visit: flat index + 4-bit slot fields, 24 B for <= 32 neighbours, 56 B for <= 96) and writes the CSR values
     B_elem = 8 * 10 / 2 + nnode_per_elem * 48 + 8.0 * ndof * ndof + 8.0 * ndof
-    B_csr = 8.0 * ndof * ndof + 2.0 * 10 * 10 + 8.0 * nnz / nelem_local
+    B_csr = 8.0 * ndof * ndof + 36.0 * 10 + 8.0 * nnz / nelem_local
     kernels = [
         {"kernel": "implicit_iso_warp_kernel<10,8>", "kernel_ms": float(k_elem), "design_bytes_per_element": B_elem,
          "design_GBps": B_elem * nelem_local / (k_elem * 1e-3) / 1e9, "traffic": traffic.get("implicit_iso_warp_kernel_bytes_per_launch"),
          "share_of_step": float(k_elem / k_step)},
-        {"kernel": "csr_gather_kernel<3,10>", "kernel_ms": float(k_csr), "design_bytes_per_element": B_csr,
-         "design_GBps": B_csr * nelem_local / (k_csr * 1e-3) / 1e9, "traffic": traffic.get("csr_gather_kernel_bytes_per_launch"),
+        {"kernel": "csr_gather_curve_kernel<10>", "kernel_ms": float(k_csr), "design_bytes_per_element": B_csr,
+         "design_GBps": B_csr * nelem_local / (k_csr * 1e-3) / 1e9, "traffic": traffic.get("csr_gather_curve_kernel_bytes_per_launch"),
          "share_of_step": float(k_csr / k_step)},
-        {"kernel": "gather_nodes_kernel<3>", "kernel_ms": float(k_T), "traffic": traffic.get("gather_nodes_kernel_bytes_per_launch"),
+        {"kernel": "gather_traction_kernel", "kernel_ms": float(k_T), "traffic": traffic.get("gather_traction_kernel_bytes_per_launch"),
          "share_of_step": float(k_T / k_step)}]
     for kk in kernels:
         if "design_GBps" in kk:

@@ -13,14 +13,15 @@
 namespace fl {
 
 namespace {
-
 struct Buf {
     void* p = nullptr;
     ~Buf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes > 0 ? bytes : 8); }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+}  // namespace
 
+namespace {
 struct Layout {   // run-time twin of gather_cfg
     int nvar, bits, fpw, fwg, maxg;
     __host__ __device__ int groups(int64_t nbr) const { return (int)((nbr + GATHER_SLOTS - 1) / GATHER_SLOTS); }
@@ -32,7 +33,9 @@ struct Layout {   // run-time twin of gather_cfg
     __host__ __device__ int64_t item_words_before(int t) const { return (int64_t)t * rw(maxg); }
 };
 
-Layout make_layout(int nvar, int bits) {
+}  // namespace
+
+static Layout make_layout(int nvar, int bits) {
     Layout L;
     L.nvar = nvar; L.bits = bits; L.fpw = 32 / bits; L.fwg = GATHER_SLOTS / L.fpw; L.maxg = nvar <= 3 ? 3 : 1;
     return L;
@@ -143,14 +146,14 @@ csr_gather_reg_kernel(const GatherPlan gp, const double* __restrict__ ke, double
     gather_warp_loop<NV, BITS, gather_batch<NV, NPE>::B, NPE, false>(gp, wid, nw, ke, V, lane, *sm, nullptr, 0, nullptr);
 }
 
-int bits_for(int nvar, int npe) {
+static int bits_for(int nvar, int npe) {
     if (nvar == 2) return npe <= 15 ? 4 : 0;
     if (nvar == 3) return (npe <= 15 && npe % 2 == 0) ? 4 : 0;   // odd node counts: 72*npe bytes per row block is not a multiple of 16
     if (nvar == 4) return npe <= 255 ? 8 : 0;
     return 0;
 }
 
-bool shape_instantiated(int nvar, int npe) {
+static bool shape_instantiated(int nvar, int npe) {
     if (nvar == 2) return npe == 3 || npe == 4 || npe == 6 || npe == 9;
     if (nvar == 3) return npe == 4 || npe == 8 || npe == 10;
     if (nvar == 4) return npe == 4 || npe == 8 || npe == 10 || npe == 27;
@@ -158,7 +161,7 @@ bool shape_instantiated(int nvar, int npe) {
 }
 
 template <int NV, int BITS, int NPE>
-int launch_T(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
+static int launch_T(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     using SM = gather_warp_smem<NV, BITS, gather_batch<NV, NPE>::B, NPE>;
     auto kern = csr_gather_reg_kernel<NV, BITS, NPE>;
     const size_t smem = sizeof(SM) * GW;
@@ -174,8 +177,6 @@ int launch_T(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
 }
-
-}  // namespace
 
 void gather_plan_release(GatherPlan& g) {
     cudaFree(g.items); cudaFree(g.recs);

@@ -26,13 +26,13 @@
 namespace fl {
 
 namespace {
-
 struct Buf {
     void* p = nullptr;
     ~Buf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes > 0 ? bytes : 8); }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+}  // namespace
 
 __global__ void positions_kernel(const int64_t* __restrict__ perm, int64_t nelem, int32_t* __restrict__ pos) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -101,7 +101,7 @@ __global__ void gather_traction_kernel(const int64_t* __restrict__ adj_ptr, cons
     for (int i = 0; i < 3; ++i) T[n * 3 + i] = acc[i];
 }
 
-int plan_build(fl_handle* h) {
+static int plan_build(fl_handle* h) {
     StreamPlan& sp = h->splan;
     const int npe = h->npe;
     const int64_t nelem = h->nelem, nvisit = nelem * npe;
@@ -144,7 +144,7 @@ int plan_build(fl_handle* h) {
 }
 
 template <int NPE>
-int launch_T(fl_handle* h, const double* Eulerx, const MatParams& prm, int update, double* V, double* T, cudaStream_t st) {
+static int launch_T(fl_handle* h, const double* Eulerx, const MatParams& prm, int update, double* V, double* T, cudaStream_t st) {
     using S = iso_warp_shape<NPE, 8>;
     StreamPlan& sp = h->splan;
     sp.epoch = sp.epoch == INT32_MAX ? 1 : sp.epoch + 1;
@@ -192,8 +192,6 @@ int launch_T(fl_handle* h, const double* Eulerx, const MatParams& prm, int updat
     return FL_OK;
 }
 
-}  // namespace
-
 void stream_plan_free(fl_handle* h) {
     StreamPlan& sp = h->splan;
     if (sp.side) { cudaStreamSynchronize(sp.side); cudaStreamDestroy(sp.side); }
@@ -210,7 +208,7 @@ bool stream_csr_supported(const fl_handle* h) {
 }
 
 // Error flag of the most recent streamed call(s): blocks until the stream has drained (debugging / tests only).
-int stream_check(fl_handle* h, cudaStream_t st) {
+static int stream_check(fl_handle* h, cudaStream_t st) {
     if (!h->splan.err) return FL_OK;
     int32_t e = 0;
     FL_CUDA_CHECK(cudaMemcpyAsync(&e, h->splan.err, sizeof(e), cudaMemcpyDeviceToHost, st));
