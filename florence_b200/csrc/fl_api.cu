@@ -338,7 +338,7 @@ int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Euler
     }
     // CSR mode with the DMMA kernel of p = 3 hexahedra: the K_e scratch is laid out as dof-pair planes (full-sector fragment stores);
     // the wide CSR reduction reads the same layout.  COO mode always keeps the reference's element-major triplet order.
-    h->ke_plane_major = (mode == FL_MODE_CSR && h->ndim == 3 && h->use_mma_implicit && h->npe == 64 && h->ng == 64) ? 1 : 0;
+    h->ke_plane_major = (mode == FL_MODE_CSR && h->ndim == 3 && h->use_mma_implicit && h->npe == 64 && h->ng == 64) ? (h->use_mma_implicit == 3 ? 1 : 2) : 0;
     mark(h, 0, st);
     rc = launch_implicit_elements(h, Eulerx, Eulerp, mat, formulation_number, requires_geometry_update ? 1 : 0, ke, h->te, st);
     if (rc) return rc;

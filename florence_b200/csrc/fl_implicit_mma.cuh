@@ -383,7 +383,13 @@ implicit_mma_gemm_kernel(const double* __restrict__ jmT, const double* __restric
                                 const int b = 8 * nt + 2 * lc + z;
                                 if (b < NPE && !(symp && a > b)) {
                                     const bool mirror = (i != j) || (symp && a != b);
-                                    if (plane_major) {
+                                    if (plane_major == 2) {
+                                        // K_e scratch as per-row-node planes [a][(i,j)][b]: the same 64-byte fragment rows and
+                                        // columns as below, and the NV*NV plane rows of one row node -- what one visit of the CSR
+                                        // reduction reads -- are one contiguous run of NV*NV*NPE doubles
+                                        Ke[((size_t)a * (NV * NV) + (i * NV + j)) * NPE + b] = c[m][q][z];
+                                        if (mirror) Ke[((size_t)b * (NV * NV) + (j * NV + i)) * NPE + a] = c[m][q][z];
+                                    } else if (plane_major) {
                                         // K_e scratch as dof-pair planes [(i,j)][a][b]: the 4 lanes of a fragment row write 64
                                         // contiguous bytes, and so do the 8 lanes of a fragment column in the mirror plane
                                         Ke[((size_t)(i * NV + j) * NPE + a) * NPE + b] = c[m][q][z];

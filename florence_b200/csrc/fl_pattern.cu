@@ -426,6 +426,10 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
             const int64_t flat = flats[v];
             const int64_t e = flat / npe;
             const int a = (int)(flat - e * npe);
+            if (plane_major == 2) {
+                // per-row-node planes [a][(i,l)][b]: the whole visit is one contiguous run
+                return e * (int64_t)ndof * ndof + (int64_t)a * (NV * NV) * npe + t;
+            }
             if (plane_major) {
                 // K_e scratch stored as dof-pair planes [(i,l)][a][b] (DMMA element kernels): npe-long contiguous runs
                 const int il = t / npe, b = t - il * npe;
@@ -445,7 +449,40 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
             const int b = c / NV, l = c - b * NV;
             return i * w + (int)rk[b] * NV + l;
         };
-        if (run <= MAXR * (int)blockDim.x) {
+        if (NPE_T == 64 && NV == 4 && plane_major && blockDim.x == 256) {
+            // hex64 / nvar 4, dof-pair planes: warp w owns planes 2w and 2w+1 outright (128 items per visit = 4 per lane), so the
+            // destinations of different warps never meet and the visits are ordered by __syncwarp alone -- no block barrier per visit
+            // (ncu: 3.0 barrier stalls per issue with the items dealt round-robin over the block)
+            const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+            const int cn = w / NV;
+            int il[4], bb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { il[u] = 2 * wp + (u >> 1); bb[u] = ln + 32 * (u & 1); }
+            auto src = [&](int v, int u) -> int64_t {
+                const int64_t flat = flats[v];
+                const int64_t e = flat >> 6;
+                const int a = (int)(flat & 63);
+                return plane_major == 2 ? e * (int64_t)(256 * 256) + ((int64_t)a * 16 + il[u]) * 64 + bb[u]
+                                        : e * (int64_t)(256 * 256) + ((int64_t)il[u] * 64 + a) * 64 + bb[u];
+            };
+            double nxt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nxt[u] = nvis > 0 ? ke[src(0, u)] : 0.0;
+            for (int v = 0; v < nvis; ++v) {
+                double cur[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+                if (v + 1 < nvis) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nxt[u] = ke[src(v + 1, u)];
+                }
+                const uint16_t* rk = rks + v * 64;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rowbuf[il[u] * cn + (int)rk[bb[u]]] += cur[u];
+                __syncwarp();
+            }
+            __syncthreads();
+        } else if (run <= MAXR * (int)blockDim.x) {
             double nxt[MAXR];
 #pragma unroll
             for (int u = 0; u < MAXR; ++u) {

@@ -33,6 +33,15 @@ def test_config2_tet10_linear_elastic_1M_elements():
     V, T = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
     V2, T2 = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
     assert torch.equal(V, V2) and torch.equal(T, T2)            # deterministic reduction
+    # the default path stores K_e along the Morton curve and reduces it with the register-resident gather (fl_stream.cu): at full
+    # size it must equal, bit for bit, the element-order path with the shared-memory row-buffer reduction, and the register gather
+    # in element order
+    for o3, o4 in ((0, 0), (1, 0)):
+        h.set_option(3, o3); h.set_option(4, o4)
+        V2, T2 = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+        assert torch.equal(V, V2) and torch.equal(T, T2), (o3, o4)
+    h.set_option(3, 0); h.set_option(4, 1)
+    del V2, T2
     K = torch.sparse_csr_tensor(indptr.long(), indices.long(), V, size=(nrow, nrow))
     scale = float(V.abs().max())
     # rigid translations are in the null space of K (row sums of each displacement component vanish)
