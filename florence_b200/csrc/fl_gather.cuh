@@ -1,10 +1,10 @@
-// fl_gather.cuh -- register-resident CSR value reduction fed by asynchronous copies ("column-owner gather").
+// fl_gather.cuh -- register-resident CSR value reduction fed by asynchronous copies ("slot-owner gather").
 //
 // Same sum as csr_gather_kernel (fl_pattern.cu) and the reference's slot-map scatter (SparseAssemblyNative.h:32-45,
 // _MassIntegrand_.h:115-166): the NV rows of node n in V are the sum, over the elements of n in ascending order, of the NV rows of
 // K_e that belong to n, placed by the rank of the column node.  The shared-memory row buffer of csr_gather_kernel costs ~400
 // shared-memory wavefronts per tet10 element, 44 % of them bank conflicts of the rank-scattered read-modify-writes
-// (profiles/r1_summary.md).  Here the roles are turned round: a lane OWNS CSR columns and pulls what belongs to them.
+// (profiles/r1_summary.md).  Here the roles are turned round: a lane OWNS a node slot of the CSR rows and pulls what belongs to it.
 //
 //   work item  = (node n, up to 96 consecutive node slots of its neighbour list = up to 3 groups of 32 slots); one warp per item
 //   lane       = slot 32 g + lane of the item; accumulators acc[g][i][j] for the NV x NV block of that slot in registers
@@ -41,8 +41,8 @@ struct GatherStep {   // what the three pipeline stages of a warp pass to each o
 };
 
 // Depth of the per-warp software pipeline, in steps: at iteration s the records of step s + GP_DR are requested (cp.async), the
-// row blocks of step s + GP_DW are requested (cp.async.cg, 16-byte pieces) and step s is reduced.  The item descriptors are requested GP_DI items
-// ahead.  A warp that owns few registers and runs beside the element kernel has no other way of covering the latencies: nothing it
+// row blocks of step s + GP_DW are requested (cp.async.cg, 16-byte pieces) and step s is reduced.  The item descriptors are
+// requested GP_DI items ahead.  A warp that owns few registers and runs beside the element kernel has no other way of covering the latencies: nothing it
 // waits for may have been requested less than a few steps ago.
 constexpr int GP_DR = 4, GP_DW = 1, GP_NROW = GP_DW + 1, GP_NREC = 8, GP_DI = GP_DR - GP_DW + 1, GP_NDESC = 8;
 static_assert(GP_NREC >= GP_DR + 2 && (GP_NREC & (GP_NREC - 1)) == 0 && GP_NDESC >= GP_DI + 1, "ring sizes");
