@@ -14,7 +14,10 @@ mat = backend.make_material(10, 0.0, mu=1e5, lamb=1.5e5)
 nnz = h.build_pattern(3)
 V = torch.empty(nnz, dtype=torch.float64, device=dev); T = torch.empty(pts.shape[0] * 3, dtype=torch.float64, device=dev)
 out = {}
+only = os.environ.get("FL_ONLY")
 for name, o3, o4 in (("element order, smem gather", 0, 0), ("element order, reg gather", 1, 0), ("curve order, two-pass", 0, 1), ("curve, flags, sequential", 0, 3), ("curve, concurrent", 0, 2)):
+    if only and only not in name and name != "element order, smem gather":
+        continue
     h.set_option(3, o3); h.set_option(4, o4)
     t0 = time.perf_counter()
     h.assemble_implicit(x, None, mat, 0, True, mode="csr", out=(V, T)); torch.cuda.synchronize()
