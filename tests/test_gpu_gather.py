@@ -108,3 +108,73 @@ def test_curve_ordered_assembly_equals_element_order_assembly(kind, p, n, nel):
     h.set_option(4, 1)
     h.set_option(2, 1)
     h.close()
+
+
+def test_register_gather_on_a_fan_of_tetrahedra():
+    """One node shared by 150 tet4 elements with ~190 neighbours: several items per node (more than 96 slots), records fetched in
+    more than one batch of 32 visits, many steps per item -- against the row-buffer reduction (bit for bit) and the oracle."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    rng = np.random.default_rng(7)
+    nnode, nelem = 200, 150
+    pts = rng.random((nnode, 3))
+    els = np.zeros((nelem, 4), dtype=np.int64)
+    for e in range(nelem):
+        els[e, 0] = 0
+        els[e, 1:] = rng.choice(np.arange(1, nnode), 3, replace=False)
+    for e in range(nelem):                      # positive orientation, so that the kinematics are the ordinary ones
+        X = pts[els[e]]
+        if np.linalg.det(X[1:] - X[0]) < 0:
+            els[e, [2, 3]] = els[e, [3, 2]]
+    B, Jm, AG = flmesh.tables("tet", 1)
+    x = pts + 0.01 * np.sin(5 * pts + 0.3)
+    h = backend.AssemblyHandle(pts, els, Jm, AG, B)
+    mat = backend.make_material(10, 1.0, mu=3.0, lamb=7.0)
+    prm = orc.params(mu=3.0, lamb=7.0)
+    pat = orc.sparsity_pattern(els, nnode, 3)
+    Vo, To = orc.assemble_implicit(pts, els, x, None, Jm, AG, 3, 6, 1, prm, 10, mode="csr", pattern=pat)
+    h.build_pattern(3)
+    out = {}
+    for opt in (0, 1):
+        h.set_option(3, opt)
+        V, T = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+        out[opt] = V.clone()
+        assert np.abs(V.cpu().numpy() - Vo).max() <= 1e-10 * np.abs(Vo).max()
+        assert np.linalg.norm(T.cpu().numpy() - To) <= 1e-11 * np.linalg.norm(To)
+    assert torch.equal(out[0], out[1])
+    h.close()
+
+
+def test_curve_ordered_assembly_with_shuffled_renumbered_and_repeated_elements():
+    """Nothing may depend on the mesh's own ordering: tet10 mesh with randomly renumbered nodes, shuffled elements and every element
+    listed five times (vertex nodes are then visited 120 times: several batches of records, twenty steps) -- all curve-ordered modes
+    against the element-order path (bit for bit) and the oracle."""
+    from florence_b200 import backend, mesh as flmesh
+    from oracle import oracle as orc
+    os.environ["FL_STREAM_CHECK"] = "1"
+    rng = np.random.default_rng(11)
+    pts, els = flmesh.box_tet_mesh(3, 3, 3, p=2)
+    pts, els = pts.numpy(), els.numpy()
+    perm = rng.permutation(pts.shape[0])                  # new id of old node k
+    P = np.empty_like(pts); P[perm] = pts
+    E = perm[els]
+    E = np.concatenate([E] * 5)[rng.permutation(5 * els.shape[0])]
+    B, Jm, AG = flmesh.tables("tet", 2)
+    x = P + 0.004 * np.sin(7 * P + 1.0)
+    h = backend.AssemblyHandle(P, E, Jm, AG, B)
+    mat = backend.make_material(10, 1.0, mu=3.0, lamb=7.0)
+    prm = orc.params(mu=3.0, lamb=7.0)
+    pat = orc.sparsity_pattern(E, P.shape[0], 3)
+    Vo, To = orc.assemble_implicit(P, E, x, None, Jm, AG, 3, 6, 1, prm, 10, mode="csr", pattern=pat)
+    h.build_pattern(3)
+    h.set_option(4, 0)
+    Vr, Tr = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+    Vr, Tr = Vr.clone(), Tr.clone()
+    assert np.abs(Vr.cpu().numpy() - Vo).max() <= 1e-10 * np.abs(Vo).max()
+    assert np.linalg.norm(Tr.cpu().numpy() - To) <= 1e-11 * np.linalg.norm(To)
+    for mode in (1, 2, 3):
+        h.set_option(4, mode)
+        V, T = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
+        assert torch.equal(V, Vr) and torch.equal(T, Tr), "mode %d" % mode
+    h.set_option(4, 1)
+    h.close()
