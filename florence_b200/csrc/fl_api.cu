@@ -168,7 +168,7 @@ int fl_set_option(fl_handle* h, int option, int value) {
     if (option == 0) { h->use_mma = value ? 1 : 0; return FL_OK; }
     if (option == 1) { h->use_mma_implicit = value; return FL_OK; }
     if (option == 2) { h->use_warp_iso = value; return FL_OK; }
-    if (option == 3) { h->use_reg_gather = value ? 1 : 0; return FL_OK; }
+    if (option == 3) { h->use_reg_gather = value; return FL_OK; }
     if (option == 4) { h->use_stream = value; return FL_OK; }
     set_error("unknown option %d", option);
     return FL_ERR_INVALID;
@@ -225,7 +225,7 @@ int fl_pattern_build(fl_handle* h, int nvar, int64_t* nnz_host) {
     int rc = pattern_build(h);
     if (rc) return rc;
     // the plan of the register-resident CSR reduction depends on the pattern and nvar only: built here, outside the assembly calls
-    if (h->use_reg_gather && reg_gather_supported(h, nvar)) {
+    if (reg_gather_preferred(h, nvar)) {
         rc = gather_plan_ensure(h, nvar);
         if (rc) return rc;
     }

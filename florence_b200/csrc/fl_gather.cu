@@ -190,6 +190,16 @@ bool reg_gather_supported(const fl_handle* h, int nvar) {
            h->nelem > 0 && h->nelem * (int64_t)h->npe < ((int64_t)1 << 31);
 }
 
+// Where the register gather beats the row-buffer kernels in element order (profiles/gather_shapes_bench.py, 0.5-3 M elements, B200):
+// every 2-D shape (tri3 3.0x, tri6 2.7x, quad4 1.3x, quad9 2.6x), hex8 with nvar = 3 (1.23x) and tet10 with nvar = 4 (2.9x); it is
+// slower for tet4 (0.8x) and tet10 with nvar = 3 (0.9x) and equal for hex8 / hex27 with nvar = 4.
+bool reg_gather_preferred(const fl_handle* h, int nvar) {
+    if (!reg_gather_supported(h, nvar)) return false;
+    if (h->use_reg_gather == 1) return true;
+    if (h->use_reg_gather != 2) return false;
+    return nvar == 2 || (nvar == 3 && h->npe == 8) || (nvar == 4 && h->npe == 10);
+}
+
 int gather_plan_ensure(fl_handle* h, int nvar) {
     if (h->gplan.nvar == nvar && h->gplan.recs) return FL_OK;
     return gather_plan_build(h, nvar, nullptr, false, &h->gplan);

@@ -123,8 +123,9 @@ struct fl_handle {
     int use_stream = 1;          // LinearElastic tet10 (hex8 with option 2 = 2) in CSR mode (fl_stream.cu, fl_set_option 4): 1 = K_e along
                                  // a space-filling curve, reduction in completion order; 2 = the same with both kernels running
                                  // concurrently (measured slower); 3 = the kernels of 2 one after the other; 0 = off
-    int use_reg_gather = 0;      // CSR value reduction of the element-order paths: 1 = register-resident slot-owner gather
-                                 // (fl_gather.cuh), 0 = shared-memory row-buffer kernels of fl_pattern.cu (fl_set_option 3)
+    int use_reg_gather = 2;      // CSR value reduction of the element-order paths (fl_set_option 3): 1 = register-resident slot-owner
+                                 // gather (fl_gather.cuh) wherever it is instantiated, 0 = shared-memory row-buffer kernels of
+                                 // fl_pattern.cu, 2 = whichever was measured faster for the shape (reg_gather_preferred)
     double* ch = nullptr;  size_t ch_bytes = 0;   // per-element Chat_g blocks between the prologue and the DMMA kernel (p >= 2 hexahedra)
     int32_t* flag = nullptr;                       // device status: [0] bit 0 NaN, bit 1 growth blow-up; [1] increment of first detection
     int64_t* growth = nullptr;                     // running maxima (ordered keys) of U and U0 for the blow-up test
@@ -181,6 +182,7 @@ void gather_plan_free(fl_handle* h);
 void gather_plan_release(GatherPlan& g);
 int gather_plan_build(fl_handle* h, int nvar, const int32_t* flat_store, bool by_completion, GatherPlan* out);
 bool reg_gather_supported(const fl_handle* h, int nvar);
+bool reg_gather_preferred(const fl_handle* h, int nvar);
 int gather_plan_ensure(fl_handle* h, int nvar);
 int launch_csr_gather_reg(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st);
 // fl_stream.cu

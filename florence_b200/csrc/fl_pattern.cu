@@ -594,7 +594,7 @@ static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaS
 
 int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st) {
     if (!h->pat.nbr_ptr) { set_error("fl_pattern_build has not been called"); return FL_ERR_STATE; }
-    if (h->use_reg_gather && reg_gather_supported(h, nvar)) return launch_csr_gather_reg(h, nvar, ke, V, st);
+    if (reg_gather_preferred(h, nvar)) return launch_csr_gather_reg(h, nvar, ke, V, st);
     switch (nvar) {
         case 1: return launch_csr_gather_NV<1>(h, ke, V, st);
         case 2: return launch_csr_gather_NV<2>(h, ke, V, st);

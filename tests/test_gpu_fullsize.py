@@ -40,7 +40,7 @@ def test_config2_tet10_linear_elastic_1M_elements():
         h.set_option(3, o3); h.set_option(4, o4)
         V2, T2 = h.assemble_implicit(x, None, mat, 0, True, mode="csr")
         assert torch.equal(V, V2) and torch.equal(T, T2), (o3, o4)
-    h.set_option(3, 0); h.set_option(4, 1)
+    h.set_option(3, 2); h.set_option(4, 1)
     del V2, T2
     K = torch.sparse_csr_tensor(indptr.long(), indices.long(), V, size=(nrow, nrow))
     scale = float(V.abs().max())
