@@ -336,6 +336,14 @@ int fl_assemble_implicit(fl_handle* h, const double* Eulerx, const double* Euler
         mark(h, 0, st);
         return launch_stream_iso_csr(h, Eulerx, mat, requires_geometry_update ? 1 : 0, V, T, st);
     }
+    // other materials on the shapes for which it pays: the ordinary element kernel on the curve-ordered connectivity + the same reduction
+    if (mode == FL_MODE_CSR && curve_csr_preferred(h, nvar)) {
+        mark(h, 0, st);
+        rc = launch_curve_csr(h, nvar, Eulerx, Eulerp, mat, formulation_number, requires_geometry_update ? 1 : 0, V, T, st,
+                              h->timing ? h->ev[1] : nullptr, h->timing ? h->ev[2] : nullptr);
+        mark(h, 3, st);
+        return rc;
+    }
     // CSR mode with the DMMA kernel of p = 3 hexahedra: the K_e scratch is laid out as dof-pair planes (full-sector fragment stores);
     // the wide CSR reduction reads the same layout.  COO mode always keeps the reference's element-major triplet order.
     h->ke_plane_major = (mode == FL_MODE_CSR && h->ndim == 3 && h->use_mma_implicit && h->npe == 64 && h->ng == 64) ? (h->use_mma_implicit == 3 ? 1 : 2) : 0;

@@ -125,13 +125,6 @@ __global__ void record_fields_kernel(const int32_t* __restrict__ conn, const int
     atomicAnd(&rec[2 + g * L.fwg + f / L.fpw], ~(none << sh) | ((uint32_t)b << sh));
 }
 
-// visits per step: ~4.5 kB of row blocks per buffer (two buffers per warp)
-template <int NV, int NPE>
-struct gather_batch {
-    static constexpr int RAW = 4608 / (NV * NV * NPE * 8);
-    static constexpr int B = RAW < 2 ? 2 : (RAW > 8 ? 8 : RAW);
-};
-
 constexpr int GW = 8;   // warps per block of the stand-alone kernel
 
 template <int NV, int BITS, int NPE>

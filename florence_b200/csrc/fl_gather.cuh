@@ -40,6 +40,13 @@ struct GatherStep {   // what the three pipeline stages of a warp pass to each o
     int32_t nv, w, nslots, ng, flags, pad;  // flags: 1 = first step of the item, 2 = last step, 4 = no more work
 };
 
+// visits per step: ~4.5 kB of row blocks per buffer (two buffers per warp)
+template <int NV, int NPE>
+struct gather_batch {
+    static constexpr int RAW = 4608 / (NV * NV * NPE * 8);
+    static constexpr int B = RAW < 2 ? 2 : (RAW > 8 ? 8 : RAW);
+};
+
 // Depth of the per-warp software pipeline, in steps: at iteration s the records of step s + GP_DR are requested (cp.async), the
 // row blocks of step s + GP_DW are requested (cp.async.cg, 16-byte pieces) and step s is reduced.  The item descriptors are
 // requested GP_DI items ahead.  A warp that owns few registers and runs beside the element kernel has no other way of covering the latencies: nothing it

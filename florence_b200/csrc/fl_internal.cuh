@@ -71,7 +71,7 @@ struct GatherPlan {
 // Curve-ordered CSR assembly (fl_stream.cu): the element kernel walks the elements in space-filling-curve order; the CSR reduction
 // follows in completion order, optionally beside it on a second stream (then the element kernel publishes its progress).
 struct StreamPlan {
-    int npe = 0;
+    int npe = 0, nvar = 0;
     int64_t ngroups = 0;
     int32_t* conn_p = nullptr;      // connectivity in storage (curve) order
     int32_t* adj_idx_p = nullptr;   // adjacency (node -> visits, ascending ORIGINAL element number) as storage flat indices
@@ -189,6 +189,9 @@ int launch_csr_gather_reg(fl_handle* h, int nvar, const double* ke, double* V, c
 void stream_plan_free(fl_handle* h);
 bool stream_csr_supported(const fl_handle* h);
 int launch_stream_iso_csr(fl_handle* h, const double* Eulerx, const fl_material* mat, int update, double* V, double* T, cudaStream_t st);
+bool curve_csr_preferred(const fl_handle* h, int nvar);
+int launch_curve_csr(fl_handle* h, int nvar, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation, int update,
+                     double* V, double* T, cudaStream_t st, cudaEvent_t after_elements, cudaEvent_t after_reduction);
 // fl_dirichlet.cu
 void dirichlet_free(fl_handle* h);
 int dirichlet_build(fl_handle* h, int nvar, const int32_t* cols_out, int64_t n_out);

@@ -85,27 +85,43 @@ csr_gather_curve_kernel(const GatherPlan gp, const double* __restrict__ ke, doub
     gather_warp_loop<3, 4, 6, NPE, false>(gp, wid, nw, ke, V, lane, *sm, nullptr, 0, nullptr);
 }
 
+// Any material / element kernel (launch_curve_csr): the same reduction for every (nvar, nodes per element) the gather is instantiated for
+template <int NV, int BITS, int NPE>
+__global__ void __launch_bounds__(256)
+csr_gather_curve_any_kernel(const GatherPlan gp, const double* __restrict__ ke, double* __restrict__ V) {
+    using SM = gather_warp_smem<NV, BITS, gather_batch<NV, NPE>::B, NPE>;
+    extern __shared__ __align__(16) unsigned char smem_s[];
+    SM* sm = reinterpret_cast<SM*>(smem_s) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    gather_warp_loop<NV, BITS, gather_batch<NV, NPE>::B, NPE, false>(gp, wid, nw, ke, V, lane, *sm, nullptr, 0, nullptr);
+}
+
 // T[n] = sum over the visits of node n (ascending original element number) of the per-element tractions stored in curve order
+template <int NV>
 __global__ void gather_traction_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx_p, const double* __restrict__ te,
                                        int64_t nnode, double* __restrict__ T) {
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= nnode) return;
-    double acc[3] = {0.0, 0.0, 0.0};
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
     const int64_t k1 = adj_ptr[n + 1];
     for (int64_t k = adj_ptr[n]; k < k1; ++k) {
         const int64_t idx = adj_idx_p[k];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) acc[i] += te[idx * 3 + i];
+        for (int i = 0; i < NV; ++i) acc[i] += te[idx * NV + i];
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) T[n * 3 + i] = acc[i];
+    for (int i = 0; i < NV; ++i) T[n * NV + i] = acc[i];
 }
 
-static int plan_build(fl_handle* h) {
+static int plan_build(fl_handle* h, int nvar) {
     StreamPlan& sp = h->splan;
     const int npe = h->npe;
     const int64_t nelem = h->nelem, nvisit = nelem * npe;
-    const int epw = 32 / (npe / 2);
+    const int epw = npe >= 2 ? 32 / (npe / 2) : 32;   // element-kernel group (only the iso path publishes flags)
     Buf perm, pos;
     auto fail = [&](int code) { stream_plan_free(h); return code; };
 #define FL_STRY(expr)                                                                             \
@@ -126,7 +142,7 @@ static int plan_build(fl_handle* h) {
     permute_conn_kernel<<<(unsigned)((nvisit + 255) / 256), 256>>>(h->conn, perm.as<int64_t>(), nelem, npe, sp.conn_p);
     permute_adj_kernel<<<(unsigned)((nvisit + 255) / 256), 256>>>(h->adj_idx, pos.as<int32_t>(), nvisit, npe, sp.adj_idx_p);
     FL_STRY(cudaGetLastError());
-    rc = gather_plan_build(h, 3, sp.adj_idx_p, true, &sp.gp);
+    rc = gather_plan_build(h, nvar, sp.adj_idx_p, true, &sp.gp);
     if (rc) return fail(rc);
     sp.ngroups = (nelem + epw - 1) / epw;
     FL_STRY(cudaMalloc(&sp.flags, sizeof(int32_t) * (sp.ngroups + 1)));
@@ -139,6 +155,7 @@ static int plan_build(fl_handle* h) {
     FL_STRY(cudaDeviceSynchronize());
 #undef FL_STRY
     sp.npe = npe;
+    sp.nvar = nvar;
     sp.epoch = 0;
     return FL_OK;
 }
@@ -186,7 +203,7 @@ static int launch_T(fl_handle* h, const double* Eulerx, const MatParams& prm, in
         FL_CUDA_CHECK(cudaStreamWaitEvent(st, sp.join, 0));
     }
     if (h->timing && h->ev[2]) cudaEventRecord(h->ev[2], st);
-    gather_traction_kernel<<<(unsigned)((h->nnode + 255) / 256), 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T);
+    gather_traction_kernel<3><<<(unsigned)((h->nnode + 255) / 256), 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T);
     FL_CUDA_CHECK(cudaGetLastError());
     if (h->timing && h->ev[3]) cudaEventRecord(h->ev[3], st);
     return FL_OK;
@@ -222,9 +239,9 @@ static int stream_check(fl_handle* h, cudaStream_t st) {
 }
 
 int launch_stream_iso_csr(fl_handle* h, const double* Eulerx, const fl_material* mat, int update, double* V, double* T, cudaStream_t st) {
-    if (h->splan.npe != h->npe) {
+    if (h->splan.npe != h->npe || h->splan.nvar != 3) {
         stream_plan_free(h);
-        int rc = plan_build(h);
+        int rc = plan_build(h, 3);
         if (rc) return rc;
     }
     MatParams p;
@@ -234,6 +251,62 @@ int launch_stream_iso_csr(fl_handle* h, const double* Eulerx, const fl_material*
     if (rc) return rc;
     // FL_STREAM_CHECK (tests): wait for the call and turn a raised error flag into an error code
     return (h->use_stream >= 2 && getenv("FL_STREAM_CHECK") != nullptr) ? stream_check(h, st) : FL_OK;
+}
+
+// ---- any material: element kernel of the ordinary dispatch on the curve-ordered connectivity + the reduction in completion order
+template <int NV, int BITS, int NPE>
+static int launch_curve_gather(fl_handle* h, double* V, cudaStream_t st) {
+    using SM = gather_warp_smem<NV, BITS, gather_batch<NV, NPE>::B, NPE>;
+    auto kern = csr_gather_curve_any_kernel<NV, BITS, NPE>;
+    const size_t smem = sizeof(SM) * 8;
+    FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    if (occ < 1) occ = 1;
+    kern<<<occ * h->sm_count, 256, smem, st>>>(h->splan.gp, h->ke, V);
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
+}
+
+// Shapes for which K_e along the curve + the register gather in completion order was measured faster than the best element-order
+// reduction (profiles/gather_shapes_bench.py)
+bool curve_csr_preferred(const fl_handle* h, int nvar) {
+    if (h->use_stream != 1 || h->ke_plane_major || !reg_gather_supported(h, nvar)) return false;
+    if (getenv("FL_CURVE_ALL") != nullptr) return true;      // tests: every shape the gather is instantiated for
+    return nvar == 3 && h->npe == 10;                         // tet10 mechanics: reduction 1.34 -> 1.18 ms per 547 k elements; no gain elsewhere
+}
+
+int launch_curve_csr(fl_handle* h, int nvar, const double* Eulerx, const double* Eulerp, const fl_material* mat, int formulation, int update,
+                     double* V, double* T, cudaStream_t st, cudaEvent_t after_elements, cudaEvent_t after_reduction) {
+    if (h->splan.npe != h->npe || h->splan.nvar != nvar) {
+        stream_plan_free(h);
+        int rc = plan_build(h, nvar);
+        if (rc) return rc;
+    }
+    StreamPlan& sp = h->splan;
+    int32_t* conn = h->conn;
+    h->conn = sp.conn_p;                       // the element kernels walk the elements in storage (curve) order
+    int rc = launch_implicit_elements(h, Eulerx, Eulerp, mat, formulation, update, h->ke, h->te, st);
+    h->conn = conn;
+    if (rc) return rc;
+    if (after_elements) cudaEventRecord(after_elements, st);
+    rc = FL_ERR_UNSUPPORTED;
+#define FL_CCASE(NV_, BITS_, NPE_) \
+    if (nvar == NV_ && h->npe == NPE_) rc = launch_curve_gather<NV_, BITS_, NPE_>(h, V, st)
+    FL_CCASE(2, 4, 3); FL_CCASE(2, 4, 4); FL_CCASE(2, 4, 6); FL_CCASE(2, 4, 9);
+    FL_CCASE(3, 4, 4); FL_CCASE(3, 4, 8); FL_CCASE(3, 4, 10);
+    FL_CCASE(4, 8, 4); FL_CCASE(4, 8, 8); FL_CCASE(4, 8, 10); FL_CCASE(4, 8, 27);
+#undef FL_CCASE
+    if (rc) { if (rc == FL_ERR_UNSUPPORTED) set_error("curve-ordered CSR assembly: unsupported shape"); return rc; }
+    if (after_reduction) cudaEventRecord(after_reduction, st);
+    const unsigned nb = (unsigned)((h->nnode + 255) / 256);
+    switch (nvar) {
+        case 2: gather_traction_kernel<2><<<nb, 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+        case 3: gather_traction_kernel<3><<<nb, 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+        default: gather_traction_kernel<4><<<nb, 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+    }
+    FL_CUDA_CHECK(cudaGetLastError());
+    return FL_OK;
 }
 
 }  // namespace fl

@@ -229,7 +229,7 @@ int fl_sfc_order(const double *points, const uint64_t *elements, int64_t nelem, 
  * warp-autonomous LinearElastic kernel: 1 = tet10 (default), 2 = tet10 and hex8, 0 = off; option 3 = CSR value reduction of the
  * element-order paths: 0 = shared-memory row-buffer kernels, 1 = register-resident slot-owner gather (nvar 2..4, low-order
  * elements whose K_e row blocks are multiples of 16 bytes), 2 = whichever was measured faster for the shape (default: the gather for
- * 2-D elements, hex8 mechanics and tet10 electro-mechanics); option 4 = LinearElastic on tet10 (and hex8 when option 2 is 2) in CSR
+ * 2-D elements, hex8 mechanics and tet10 electro-mechanics); option 4 = tet10 mechanics (any material; hex8 LinearElastic when option 2 is 2) in CSR
  * mode: 1 = K_e stored along a space-filling curve and reduced in completion order (default), 2 = the same with the element kernel
  * and the reduction running concurrently on two streams (measured slower), 3 = the kernels of 2 one after the other, 0 = off. */
 int fl_set_option(fl_handle *h, int option, int value);

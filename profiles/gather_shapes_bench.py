@@ -19,10 +19,14 @@ for kind, p, n, nvar in cases:
     h = backend.AssemblyHandle(pts, els, Jm, AG, B, device=dev)
     nnz = h.build_pattern(nvar)
     V = torch.empty(nnz, dtype=torch.float64, device=dev); T = torch.empty(pts.shape[0] * nvar, dtype=torch.float64, device=dev)
-    h.set_option(4, 0)
     res = {}
-    for opt in (0, 1):
-        h.set_option(3, opt)
+    for opt in (0, 1, 2):
+        # 0 / 1: element order with the row-buffer kernels / the register gather; 2: K_e along the Morton curve + register gather
+        os.environ.pop("FL_CURVE_ALL", None)
+        if opt == 2:
+            os.environ["FL_CURVE_ALL"] = "1"
+        h.set_option(4, 1 if opt == 2 else 0)
+        h.set_option(3, min(opt, 1))
         h.assemble_implicit(x, xp, mat, form, True, mode="csr", out=(V, T)); torch.cuda.synchronize()
         h.set_timing(True)
         ts = []
@@ -30,7 +34,8 @@ for kind, p, n, nvar in cases:
             h.assemble_implicit(x, xp, mat, form, True, mode="csr", out=(V, T)); ts.append(h.get_timing())
         h.set_timing(False)
         res[opt] = (np.median(np.array(ts[1:]), axis=0), V.clone())
-    print("%-4s p=%d nvar=%d  %8d elements  element kernel %.3f ms  reduction: row buffer %.3f ms, register gather %.3f ms  identical: %s"
-          % (kind, p, nvar, els.shape[0], res[0][0][0], res[0][0][1], res[1][0][1], torch.equal(res[0][1], res[1][1])))
+    print("%-4s p=%d nvar=%d  %8d elements  element kernel %.3f ms (curve order %.3f)  reduction: row buffer %.3f ms, register gather %.3f ms, "
+          "curve order %.3f ms  identical: %s" % (kind, p, nvar, els.shape[0], res[0][0][0], res[2][0][0], res[0][0][1], res[1][0][1], res[2][0][1],
+                                                   torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], res[2][1])))
     h.close(); del V, T, h
     torch.cuda.empty_cache()

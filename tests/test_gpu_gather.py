@@ -17,6 +17,18 @@ pytestmark = pytest.mark.gpu
 from test_gpu_parity import ELEC, _cases, _load, _material  # noqa: E402
 
 
+def _select(h, opt):
+    """0: element order, row-buffer kernels; 1: element order, register gather; 2: curve order + register gather for every shape the
+    gather is instantiated for (FL_CURVE_ALL; by default only the shapes where it was measured faster); None: defaults."""
+    os.environ.pop("FL_CURVE_ALL", None)
+    if opt is None:
+        h.set_option(3, 2); h.set_option(4, 1)
+        return
+    if opt == 2:
+        os.environ["FL_CURVE_ALL"] = "1"
+    h.set_option(3, min(opt, 1)); h.set_option(4, 1 if opt == 2 else 0)
+
+
 def _supported_by_register_gather(nvar, npe):
     return (nvar == 2 and npe in (3, 4, 6, 9)) or (nvar == 3 and npe in (4, 8, 10)) or (nvar == 4 and npe in (4, 8, 10, 27))
 
@@ -36,13 +48,14 @@ def test_register_gather_equals_row_buffer_gather_on_the_golden_cases(key):
     h = backend.AssemblyHandle(c["points"], c["elements"], c["Jm"], c["AllGauss"], c["Bases"])
     mat = _material(backend, num, c["prm"])
     h.build_pattern(nvar)
-    h.set_option(4, 0)
     out = {}
-    for opt in (0, 1):
-        h.set_option(3, opt)
+    for opt in (0, 1, 2):      # row buffer, register gather (element order), K_e along the curve + register gather (any material)
+        _select(h, opt)
         V, T = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, update, mode="csr")
         out[opt] = (V.clone(), T.clone())
-    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    _select(h, None)
+    for opt in (1, 2):
+        assert torch.equal(out[0][0], out[opt][0]) and torch.equal(out[0][1], out[opt][1]), opt
     h.close()
 
 
@@ -66,15 +79,17 @@ def test_register_gather_on_larger_meshes(kind, p, n, nvar):
         xp = 0.1 * torch.sin(5.0 * pts.sum(1))
     h = backend.AssemblyHandle(pts, els, Jm, AG, B)
     h.build_pattern(nvar)
-    h.set_option(4, 0)
     out = {}
-    for opt in (0, 1, 1):
-        h.set_option(3, opt)
+    for opt in (0, 1, 2, 1, 2):
+        _select(h, opt)
         V, T = h.assemble_implicit(x, xp, mat, form, True, mode="csr")
         if opt in out:
-            assert torch.equal(V, out[opt]), "bit-reproducible"
-        out[opt] = V.clone()
-    assert out[0].abs().max() > 0 and torch.equal(out[0], out[1])
+            assert torch.equal(V, out[opt][0]) and torch.equal(T, out[opt][1]), "bit-reproducible"
+        out[opt] = (V.clone(), T.clone())
+    _select(h, None)
+    assert out[0][0].abs().max() > 0
+    for opt in (1, 2):
+        assert torch.equal(out[0][0], out[opt][0]) and torch.equal(out[0][1], out[opt][1]), opt
     h.close()
 
 
