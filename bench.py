@@ -387,7 +387,8 @@ def run_b200(args, rank, world, local_rank):
          "design_GBps": B_csr * nelem_local / (k_csr * 1e-3) / 1e9, "traffic": traffic.get("csr_gather_curve_kernel_bytes_per_launch"),
          "share_of_step": float(k_csr / k_step)},
         {"kernel": "gather_traction_kernel", "kernel_ms": float(k_T), "traffic": traffic.get("gather_traction_kernel_bytes_per_launch"),
-         "share_of_step": float(k_T / k_step)}]
+         "share_of_step": float(k_T / k_step),
+         "note": "runs on a side stream beside the CSR reduction (0.10 ms alone): kernel_ms is what is left of it after the reduction has finished"}]
     for kk in kernels:
         if "design_GBps" in kk:
             kk["design_frac_of_hbm_peak"] = kk["design_GBps"] / hbm_peak

@@ -187,11 +187,21 @@ static int launch_T(fl_handle* h, const double* Eulerx, const MatParams& prm, in
     FL_CUDA_CHECK(cudaGetLastError());
     if (h->timing && h->ev[1]) cudaEventRecord(h->ev[1], st);
     if (h->use_stream == 1) {
+        // the traction reduction only needs the element kernel: it runs on the side stream beside the CSR reduction
+        FL_CUDA_CHECK(cudaEventRecord(sp.fork, st));
+        FL_CUDA_CHECK(cudaStreamWaitEvent(sp.side, sp.fork, 0));
+        gather_traction_kernel<3><<<(unsigned)((h->nnode + 255) / 256), 256, 0, sp.side>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T);
+        FL_CUDA_CHECK(cudaGetLastError());
+        FL_CUDA_CHECK(cudaEventRecord(sp.join, sp.side));
         auto ckern = csr_gather_curve_kernel<NPE>;
         const size_t csmem = sizeof(gather_warp_smem<3, 4, 6, NPE>) * 8;
         FL_CUDA_CHECK(cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         ckern<<<2 * h->sm_count, 256, csmem, st>>>(sp.gp, h->ke, V);
         FL_CUDA_CHECK(cudaGetLastError());
+        if (h->timing && h->ev[2]) cudaEventRecord(h->ev[2], st);
+        FL_CUDA_CHECK(cudaStreamWaitEvent(st, sp.join, 0));
+        if (h->timing && h->ev[3]) cudaEventRecord(h->ev[3], st);
+        return FL_OK;
     } else if (gblocks > 0) {
         const size_t gsmem = sizeof(gather_warp_smem<3, 4, SG_B, NPE>) * SG_WARPS;
         FL_CUDA_CHECK(cudaFuncSetAttribute(gkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
@@ -290,6 +300,18 @@ int launch_curve_csr(fl_handle* h, int nvar, const double* Eulerx, const double*
     h->conn = conn;
     if (rc) return rc;
     if (after_elements) cudaEventRecord(after_elements, st);
+    {   // the traction reduction only needs the element kernel: it runs on the side stream beside the CSR reduction
+        FL_CUDA_CHECK(cudaEventRecord(sp.fork, st));
+        FL_CUDA_CHECK(cudaStreamWaitEvent(sp.side, sp.fork, 0));
+        const unsigned nb = (unsigned)((h->nnode + 255) / 256);
+        switch (nvar) {
+            case 2: gather_traction_kernel<2><<<nb, 256, 0, sp.side>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+            case 3: gather_traction_kernel<3><<<nb, 256, 0, sp.side>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+            default: gather_traction_kernel<4><<<nb, 256, 0, sp.side>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+        }
+        FL_CUDA_CHECK(cudaGetLastError());
+        FL_CUDA_CHECK(cudaEventRecord(sp.join, sp.side));
+    }
     rc = FL_ERR_UNSUPPORTED;
 #define FL_CCASE(NV_, BITS_, NPE_) \
     if (nvar == NV_ && h->npe == NPE_) rc = launch_curve_gather<NV_, BITS_, NPE_>(h, V, st)
@@ -297,15 +319,13 @@ int launch_curve_csr(fl_handle* h, int nvar, const double* Eulerx, const double*
     FL_CCASE(3, 4, 4); FL_CCASE(3, 4, 8); FL_CCASE(3, 4, 10);
     FL_CCASE(4, 8, 4); FL_CCASE(4, 8, 8); FL_CCASE(4, 8, 10); FL_CCASE(4, 8, 27);
 #undef FL_CCASE
-    if (rc) { if (rc == FL_ERR_UNSUPPORTED) set_error("curve-ordered CSR assembly: unsupported shape"); return rc; }
-    if (after_reduction) cudaEventRecord(after_reduction, st);
-    const unsigned nb = (unsigned)((h->nnode + 255) / 256);
-    switch (nvar) {
-        case 2: gather_traction_kernel<2><<<nb, 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
-        case 3: gather_traction_kernel<3><<<nb, 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
-        default: gather_traction_kernel<4><<<nb, 256, 0, st>>>(h->adj_ptr, sp.adj_idx_p, h->te, h->nnode, T); break;
+    if (rc) {
+        cudaStreamWaitEvent(st, sp.join, 0);      // never leave the side stream un-joined
+        if (rc == FL_ERR_UNSUPPORTED) set_error("curve-ordered CSR assembly: unsupported shape");
+        return rc;
     }
-    FL_CUDA_CHECK(cudaGetLastError());
+    if (after_reduction) cudaEventRecord(after_reduction, st);
+    FL_CUDA_CHECK(cudaStreamWaitEvent(st, sp.join, 0));
     return FL_OK;
 }
 
