@@ -111,9 +111,13 @@ def clear_handles():
 # Host results.  The reference returns freshly allocated numpy arrays from every call (np.zeros in the Cython wrappers,
 # _LowLevelAssemblyDF_.pyx:90-103), so callers may keep K from several assemblies alive at once (modified Newton, the K/M/D
 # combinations of the implicit dynamic integrators).  The default here is the same: every call returns arrays the caller owns.
-# The copy goes device -> pinned staging buffer -> fresh array; the staging buffers are reused and never handed out.
-# `reuse_host_buffers(True)` is the opt-in for loops that consume K before re-assembling: large results are then returned as
-# views of a 2-deep ring of pinned buffers (no 2.8 GB allocation + copy per call), valid until the next-but-one call.
+# Large results (>= 64 MiB) are LEASED pinned buffers: the array handed out is backed by page-locked memory the transfer wrote
+# directly, and a weakref finaliser returns the buffer to a free list when the caller's last reference (including views, e.g. the
+# csr_matrix built on it) is gone.  A buffer is never written while anything refers to it, so the semantics are those of a fresh
+# array, but a loop that drops K before re-assembling pays neither a 2.8 GB allocation with its 700 k first-touch page faults nor a
+# host-side copy.  At most _LEASE_MAX buffers per (dtype, size) are out at once; a caller that keeps more results alive gets ordinary
+# pageable arrays for the rest (device -> pinned staging buffer -> fresh array, pages populated while the device works).
+# `reuse_host_buffers(True)` is the older opt-in: views of a 2-deep ring of pinned buffers, valid until the next-but-one call.
 _pinned = {}
 _PINNED_RING = 2
 _reuse_host_buffers = False
@@ -126,29 +130,129 @@ def reuse_host_buffers(enabled=True):
     return prev
 
 
+_LEASE_MAX = 3
+_lease_free = {}         # (dtype, n) -> [pinned tensors not referenced by any result]
+_lease_out = {}          # (dtype, n) -> number of buffers currently backing a live result
+_lease_lock = None
+
+
+def _lease_return(key, buf):
+    with _lease_lock:
+        _lease_out[key] -= 1
+        if key not in _lease_free and len(_lease_free) >= 8:      # results of many different sizes: do not hoard pinned memory
+            _lease_free.clear()
+        free = _lease_free.setdefault(key, [])
+        if len(free) < _LEASE_MAX:
+            free.append(buf)
+
+
+def _lease(t):
+    """A pinned buffer for a result of t's size that no live array refers to, or None when _LEASE_MAX are already out."""
+    global _lease_lock
+    import threading
+    if _lease_lock is None:
+        _lease_lock = threading.Lock()
+    key = (t.dtype, t.numel())
+    with _lease_lock:
+        free = _lease_free.get(key)
+        if free:
+            buf = free.pop()
+        elif _lease_out.get(key, 0) < _LEASE_MAX:
+            buf = None
+        else:
+            return None, key
+        _lease_out[key] = _lease_out.get(key, 0) + 1
+    if buf is None:
+        try:
+            buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        except RuntimeError:                       # no page-locked memory left: fall back to pageable results
+            with _lease_lock:
+                _lease_out[key] -= 1
+            return None, key
+    return buf, key
+
+
+def _leased_array(buf, key):
+    """numpy array on a leased buffer; the buffer goes back to the free list when the array and all its views are gone."""
+    import weakref
+    arr = buf.numpy()
+    weakref.finalize(arr, _lease_return, key, buf)
+    return arr
+
+
+def release_host_buffers():
+    """Drop the free pinned result buffers (they are re-created on demand)."""
+    if _lease_lock is not None:
+        with _lease_lock:
+            _lease_free.clear()
+
+
 _BIG = 64 << 20          # bytes; below this a result is simply copied out of its staging buffer
-_CHUNK = 32 << 20        # bytes per staging chunk of the pipelined fresh-array path
+_CHUNK = 64 << 20        # bytes per staging chunk of the pipelined fresh-array path
 _stage = {}
 _pool = None
+_libc = None
 
 
-def _fresh_from_device(t):
-    """Large result -> freshly allocated numpy array the caller owns: the tensor crosses PCIe in chunks through two pinned
-    staging buffers while a few host threads copy the previous chunk into the (pageable) result, so the copy-out and most of
-    the first-touch page faults hide behind the transfer."""
+def _workers():
     global _pool
-    from concurrent.futures import ThreadPoolExecutor
+    if _pool is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _pool = ThreadPoolExecutor(max(2, min(16, len(os.sched_getaffinity(0)))))
+    return _pool
+
+
+def _populate(addr, nbytes, view):
+    """Make the pages of [addr, addr + nbytes) resident and writable: madvise(MADV_POPULATE_WRITE) (Linux >= 5.14; ctypes drops the
+    GIL), else one store per page."""
+    global _libc
+    import ctypes
+    if _libc is None:
+        try:
+            _libc = ctypes.CDLL(None, use_errno=True)
+        except OSError:
+            _libc = False
+    if _libc:
+        page = 4096
+        lo = (addr + page - 1) & ~(page - 1)
+        hi = (addr + nbytes) & ~(page - 1)
+        if hi > lo and _libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(hi - lo), 23) == 0:
+            return
+    view[::max(1, 4096 // view.itemsize)] = 0
+
+
+def _fresh_begin(n, dtype):
+    """Allocate the result array of a large transfer BEFORE the device work is queued and let the worker threads populate its pages in
+    the background: the first touch of 2.8 GB (the kernel zeroing 700 k pages) otherwise sits behind the transfer and is what bounds
+    it (profiles/host_copy_probe.py: 31-40 GB/s first touch against 57 GB/s for PCIe and 58-72 GB/s for the copy into resident pages)."""
+    out = np.empty(n, dtype=dtype)
+    pool = _workers()
+    parts = pool._max_workers
+    step = (n + parts - 1) // parts
+    base = out.__array_interface__["data"][0]
+    futs = [pool.submit(_populate, base + q * step * out.itemsize, (min((q + 1) * step, n) - q * step) * out.itemsize,
+                        out[q * step:min((q + 1) * step, n)]) for q in range(parts) if q * step < n]
+    return out, futs
+
+
+def _fresh_from_device(t, prepared=None):
+    """Large result -> freshly allocated numpy array the caller owns: the tensor crosses PCIe in chunks through two pinned
+    staging buffers while the host threads copy the previous chunk into the (pageable) result.  `prepared` = (array, futures) of
+    _fresh_begin when the caller could allocate the result before the device work."""
     flat = t.reshape(-1)
     n, isz = flat.numel(), flat.element_size()
-    out = np.empty(n, dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    npdt = torch.empty(0, dtype=t.dtype).numpy().dtype
+    if prepared is not None and prepared[0].shape[0] == n and prepared[0].dtype == npdt:
+        out, futs = prepared
+    else:
+        out, futs = _fresh_begin(n, npdt)
     per = max(1, _CHUNK // isz)
     key = (t.dtype, per)
     if key not in _stage:
         _stage[key] = [torch.empty(per, dtype=t.dtype, pin_memory=True) for _ in range(2)]
     bufs = _stage[key]
-    if _pool is None:
-        import os
-        _pool = ThreadPoolExecutor(max(2, min(8, len(os.sched_getaffinity(0)) // 2)))
+    pool = _workers()
     stream = torch.cuda.current_stream()
     pending = [None, None]          # per staging buffer: futures of the host copies still reading it
     events = [None, None]
@@ -156,9 +260,9 @@ def _fresh_from_device(t):
     def drain(k, lo, hi):
         events[k].synchronize()
         src = bufs[k].numpy()[:hi - lo]
-        parts = _pool._max_workers
+        parts = pool._max_workers
         step = (hi - lo + parts - 1) // parts
-        pending[k] = [_pool.submit(np.copyto, out[lo + q * step:min(lo + (q + 1) * step, hi)], src[q * step:min((q + 1) * step, hi - lo)])
+        pending[k] = [pool.submit(np.copyto, out[lo + q * step:min(lo + (q + 1) * step, hi)], src[q * step:min((q + 1) * step, hi - lo)])
                       for q in range(parts) if q * step < hi - lo]
 
     prev = None
@@ -179,14 +283,26 @@ def _fresh_from_device(t):
         if pending[k] is not None:
             for f in pending[k]:
                 f.result()
+    for f in futs:
+        f.result()
     return out
 
 
-def _to_host(t, tag, defer=False):
+def _to_host(t, tag, defer=False, prepared=None):
     """D2H through pinned host memory; returns a numpy array (see the ownership note above)."""
     n = t.numel()
     if not _reuse_host_buffers and n * t.element_size() >= _BIG:
-        out = _fresh_from_device(t)
+        buf, key = _lease(t)
+        if buf is not None:
+            buf.copy_(t.reshape(-1), non_blocking=True)
+            arr = _leased_array(buf, key)
+            if defer:
+                ev = torch.cuda.Event()
+                ev.record()
+                return arr, ev
+            torch.cuda.current_stream().synchronize()
+            return arr
+        out = _fresh_from_device(t, prepared)
         return (out, None) if defer else out
     key = (tag, t.dtype, n)
     ent = _pinned.get(key)
@@ -218,11 +334,12 @@ def _finish_host(buf):
     return out.copy()
 
 
-def _to_host_many(items):
+def _to_host_many(items, prepared=None):
     """D2H of several results with the copies queued back to back, small ones first: the host-side copy-out of a small result
-    (T) runs while the large one (the K values) is still crossing PCIe."""
+    (T) runs while the large one (the K values) is still crossing PCIe.  `prepared` = {tag: _fresh_begin(...)}."""
     order = sorted(range(len(items)), key=lambda i: items[i][0].numel())
-    pend = {i: _to_host(items[i][0], items[i][1], defer=True) for i in order}
+    prepared = prepared or {}
+    pend = {i: _to_host(items[i][0], items[i][1], defer=True, prepared=prepared.get(items[i][1])) for i in order}
     out = [None] * len(items)
     for i in order:
         buf, ev = pend[i]
@@ -251,10 +368,17 @@ def _implicit(matname, fields, fem_solver, function_space, formulation, mesh, ma
         if device_out:
             return I, J, V, T
         return _to_host_many([(I, "I"), (J, "J"), (V, "V"), (T, "T")])
+    prepared = None
+    if not device_out and not _reuse_host_buffers:
+        # when no leased buffer is free the caller gets a pageable K: allocate it now and populate its pages while the device works
+        nnz = h.build_pattern(h.ndim + form)
+        key = (torch.float64, nnz)
+        if nnz * 8 >= _BIG and not _lease_free.get(key) and _lease_out.get(key, 0) >= _LEASE_MAX:
+            prepared = {"V": _fresh_begin(nnz, np.float64)}
     V, T = h.assemble_implicit(x, p, mat, form, update, mode="csr")
     if device_out:
         return V, T
-    return _to_host_many([(V, "V"), (T, "T")])
+    return _to_host_many([(V, "V"), (T, "T")], prepared)
 
 
 def _stamp(matname, fields):

@@ -98,7 +98,7 @@ def install_fake(monkeypatch):
     """Route florence_b200.assembly through FakeHandle (CPU tensors, plain copies instead of pinned D2H)."""
     from florence_b200 import assembly
     monkeypatch.setattr(assembly, "AssemblyHandle", FakeHandle)
-    monkeypatch.setattr(assembly, "_to_host", lambda t, tag, defer=False: t.numpy().copy())
-    monkeypatch.setattr(assembly, "_to_host_many", lambda items: tuple(t.numpy().copy() for t, _ in items))
+    monkeypatch.setattr(assembly, "_to_host", lambda t, tag, defer=False, prepared=None: t.numpy().copy())
+    monkeypatch.setattr(assembly, "_to_host_many", lambda items, prepared=None: tuple(t.numpy().copy() for t, _ in items))
     assembly._handle_cache.clear()
     return assembly

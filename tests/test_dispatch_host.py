@@ -221,8 +221,8 @@ def _launcher_worker(rank, world, port, q):
     try:
         from florence_b200 import assembly, parallel
         assembly.AssemblyHandle = FakeHandle
-        assembly._to_host = lambda t, tag, defer=False: t.numpy().copy()
-        assembly._to_host_many = lambda items: tuple(t.numpy().copy() for t, _ in items)
+        assembly._to_host = lambda t, tag, defer=False, prepared=None: t.numpy().copy()
+        assembly._to_host_many = lambda items, prepared=None: tuple(t.numpy().copy() for t, _ in items)
         key = "asm_tet2_n2_LinearElastic"
         g, Kref, Eulerx, Eulerp = _golden(key)
         so, fs, fo, me, mat = make_objects(g, key, "LinearElastic", "mechanics", True)

@@ -130,7 +130,8 @@ def test_launchers_through_the_dispatch_on_the_device():
 
 
 def test_host_results_are_caller_owned_by_default():
-    """The reference returns fresh arrays from every call; so does the plug-in unless reuse_host_buffers(True) is set."""
+    """The reference returns fresh arrays from every call; so does the plug-in unless reuse_host_buffers(True) is set.  Large results
+    are leased pinned buffers recycled by a weakref finaliser: never while a reference or a view exists."""
     from florence_b200 import assembly
     from test_gpu_plugin import make_objects
     key = "asm_hex2_n2_NeoHookean"
@@ -146,6 +147,20 @@ def test_host_results_are_caller_owned_by_default():
         for K, d in zip(Ks, datas):
             assert np.array_equal(K.data, d)           # earlier results are not overwritten by later calls
         assert not np.array_equal(Ks[0].data, Ks[1].data)
+        # large results are leased pinned buffers: one may only be written again once the result AND every view of it are gone
+        import gc
+        view = Ks[0].data[::2]
+        keep = view.copy()
+        addr = Ks[0].data.__array_interface__["data"][0]
+        del Ks, K
+        gc.collect()
+        later = [assembly.Assemble(so, fs, fo, me, mat, g[key + "_Eulerx"] * (1.0 + 2e-3 * k), np.zeros(me.nnode))[0] for k in range(5)]
+        assert all(not np.shares_memory(view, L.data) for L in later) and np.array_equal(view, keep)
+        del view, later
+        gc.collect()
+        again = [assembly.Assemble(so, fs, fo, me, mat, g[key + "_Eulerx"], np.zeros(me.nnode))[0] for _ in range(3)]
+        assert any(A.data.__array_interface__["data"][0] == addr for A in again)     # ... and then it IS recycled
+        del again
         prev = assembly.reuse_host_buffers(True)
         a = assembly._LowLevelAssembly_Par_(so, fs, fo, me, mat, g[key + "_Eulerx"], np.zeros(me.nnode))[2]
         assembly._LowLevelAssembly_Par_(so, fs, fo, me, mat, g[key + "_Eulerx"] * 1.001, np.zeros(me.nnode))
