@@ -332,7 +332,7 @@ def run_b200(args, rank, world, local_rank):
     fresh_s = max_over_ranks(time.perf_counter() - t0)
     assert np.array_equal(held[-1][0], Vh) and not np.shares_memory(held[-1][0], held[-2][0]) and not np.shares_memory(held[-1][0], Vh)
     del held
-    launches += 6 * (e2e_steps + 2)
+    launches += 3 * (2 * e2e_steps + 5)     # (e2e_steps + 2) + (3 + e2e_steps) plug-in calls, three kernels each
     e2e_value = nelem_owned * world * e2e_steps / e2e_s
 
     # ------------------------------------------------------------------ the same Newton-iteration assembly with K kept on the device
