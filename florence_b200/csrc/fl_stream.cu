@@ -1,5 +1,6 @@
-// fl_stream.cu -- CSR assembly of the isotropic constant-tangent material (LinearElastic) on tet10 / hex8 with K_e stored along a
-// space-filling curve, and the experiment of running the element kernel and the CSR reduction CONCURRENTLY.
+// fl_stream.cu -- CSR assembly with K_e stored along a space-filling curve: the warp-autonomous LinearElastic kernel on tet10 / hex8
+// (launch_stream_iso_csr), any material through the ordinary element-kernel dispatch (launch_curve_csr), and the experiment of
+// running the element kernel and the CSR reduction CONCURRENTLY.
 //
 // Same result, bit for bit, as implicit_iso_warp_kernel followed by csr_gather_kernel (reference: _GlobalAssemblyDF_,
 // _LowLevelAssemblyDF_.h:8-176, with the slot-map scatter of SparseAssemblyNative.h:32-45).  The two-pass form writes 7.2 kB of K_e per
@@ -8,7 +9,7 @@
 //     a) of the K_e scratch; the summation order of every CSR entry stays ascending ORIGINAL element number, because the adjacency is
 //     not reordered, only the addresses it points to.
 //   * The reduction (fl_gather.cuh) walks the (node, <= 96 slots) items in the order in which the element walk completes them.
-// use_stream = 1 (default): the two kernels run one after the other.  The reduction reads the row blocks of one element, which
+// use_stream = 1 (default): the two kernels run one after the other (the traction reduction on a side stream).  The reduction reads the row blocks of one element, which
 //     straddle 128-byte lines, close together in time: 2.10 ms against 2.48 ms for csr_gather_kernel on config 2 (998 250 tet10).
 // use_stream = 2: the reduction runs on a second stream BESIDE the element kernel (4 warps per SM fit next to its two blocks: the
 //     register file holds 2 x 128 x 200 + 128 x 112), waits (acquire) for per-group release flags the element kernel publishes, and
@@ -56,7 +57,7 @@ __global__ void permute_adj_kernel(const int32_t* __restrict__ adj_idx, const in
 }
 
 constexpr int SG_WARPS = 4;   // reduction warps per SM beside the two element blocks (register file: 2 x 128 x 200 + 128 x 112)
-constexpr int SG_B = 4;       // visits per step: 3 x 4 x 720 B of row blocks per warp fit beside the element blocks' shared memory
+constexpr int SG_B = 4;       // visits per step: 2 x 4 x 720 B of row blocks per warp fit beside the element blocks' shared memory
 
 template <int NPE>
 __global__ void __maxnreg__(112)
