@@ -29,8 +29,14 @@ _I64_MIN = -(1 << 63)
 
 class ExplicitStructuralDynamicIntegrator(object):
 
-    def __init__(self, handle, material, M=None, rho=None, exchange=None, contact=None, surface_nodes=None, overlap="auto",
+    def __init__(self, handle, material, M=None, rho=None, exchange=None, contact=None, surface_nodes=None, overlap=False,
                  check_growth=True):
+        # overlap: evaluate the interface elements first and the interior ones while the messages travel (same bits either way,
+        # tests/multigpu_check.py).  Off by default: on 4 and 8 ranks the split element kernel running beside the NCCL kernels of two
+        # neighbours measured 0.1-3 ms per step SLOWER than evaluating everything and then exchanging (the point-to-point kernels
+        # hold SM slots while they wait for a late neighbour), and on 2 ranks the two orders are within 0.5 % of each other
+        # (profiles/r2_scaling_observed.json); two short tuning schemes picked the wrong order because the slowdown only develops
+        # as the ranks drift apart.
         self.h = handle
         self.mat = material
         self.exchange = exchange
@@ -120,39 +126,9 @@ class ExplicitStructuralDynamicIntegrator(object):
             ex.start(own_filled=True)
             ex.finish()
 
-    def _tune_overlap(self, x):
-        """overlap="auto": time both orders of the force evaluation and the exchange on the current state (a pure function of x:
-        it only fills the per-element forces and the interface sums, which the first update of a call does not read) and keep the
-        faster one.  Splitting the element kernel and running it beside the NCCL kernels pays for hex27-sized steps and a two-rank
-        box, but measured slower for 4 ms hex8 steps on eight ranks (profiles/r2_scaling_observed.json).  Collective: every rank
-        tunes at its first partitioned step and the decision is the same everywhere (MAX over ranks of both timings)."""
-        nb = self.exchange.part.n_interface_elements
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if not nb or not (0 < nb < self.h.nelem) or not torch.cuda.is_available() or x.device.type != "cuda":
-            return bool(nb)
-        times = []
-        for variant in (nb, None):
-            self._force_and_exchange(x, variant)                      # warm-up
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(3):
-                self._force_and_exchange(x, variant)
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        t = torch.tensor(times, dtype=torch.float64, device=x.device)
-        if multi:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        self.tuned_ms = (float(t[0]) / 3, float(t[1]) / 3)              # (overlapped, plain) per evaluation, max over ranks
-        return bool(t[0] <= t[1])
-
     def _step_partitioned(self, nsteps, increment, fext, fs0, fs1, inc_dirichlet, ds0, ds1):
         h, ex, nv = self.h, self.exchange, self.ndim
         x = self.Eulerx.view(self.nnode, nv)
-        if self.overlap == "auto":
-            self.overlap = self._tune_overlap(x)
-        nb = self.exchange.part.n_interface_elements if self.overlap else None
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.status.zero_()
         for s in range(nsteps):
@@ -167,7 +143,7 @@ class ExplicitStructuralDynamicIntegrator(object):
                 if multi:
                     dist.all_reduce(self.keys, op=dist.ReduceOp.MAX)      # U.max(), U0.max() over the whole mesh
                 h.explicit_check(self.keys, inc, self.status)
-            self._force_and_exchange(x, nb)
+            self._force_and_exchange(x, self.exchange.part.n_interface_elements if self.overlap else None)
         if nsteps > 0:
             # caller-visible T: nodal reduction, interface nodes from the ordered sums, contact at the final geometry
             h.gather_nodes(nv, self.T)
