@@ -18,7 +18,7 @@ computed).  One "step" = one full assembly (K values in CS
 N > 1 (torchrun): weak scaling, every rank assembles its own slab (+1 halo layer of elements so the CSR rows of the nodes it
 owns are complete; no data-path collective) and emits the CSR row block it owns with global column numbers (values: a slice of
 V; columns and the all_gather'ed offsets belong to the pattern and are built once); the explicit lines exchange interface forces
-over NCCL every step, overlapped with the interior elements.
+over NCCL every step (after the element forces; the order that overlaps the exchange with the interior elements is timed beside it).
 `--impl reference` times the reference algorithm (oracle port) on all host cores instead.
 """
 import argparse
@@ -462,7 +462,7 @@ def run_b200(args, rank, world, local_rank):
         part = partition.slab_partition_hex(nxy, nxy, nz_local, p, rank, world, device=dev,
                                             lengths_per_rank=(1.0, 1.0, float(nz_local) / nxy))
         if world > 1:
-            part.interface_first()      # interface elements first: their forces are exchanged while the interior ones are evaluated
+            part.interface_first()      # interface elements first, so that the overlapped order can be timed on the same partition
         Bs, Jh, AGh = flmesh.tables("hex", p)
         hh = backend.AssemblyHandle(part.points, part.elements, Jh, AGh, Bs, device=dev)
         mat_n = backend.make_material(matnum, rho, **prm)
