@@ -289,7 +289,7 @@ class InterfaceExchange(object):
         else:
             T.view(-1, self.nvar)[self.U.long()] = self.T_iface[:n * self.nvar].view(-1, self.nvar)
 
-    # ---- split-phase exchange (the explicit step overlaps it with the interior elements)
+    # ---- split-phase exchange (with overlap=True the explicit step evaluates the interior elements between start and finish)
     def start(self, own_filled=False, T=None):
         """Post the sends / receives of the partial sums in `own` (filled by the caller when own_filled, else packed from T)."""
         if not self.ranks:
