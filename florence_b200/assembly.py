@@ -176,7 +176,7 @@ def _leased_array(buf, key):
     """numpy array on a leased buffer; the buffer goes back to the free list when the array and all its views are gone."""
     import weakref
     arr = buf.numpy()
-    weakref.finalize(arr, _lease_return, key, buf)
+    weakref.finalize(arr, _lease_return, key, buf).atexit = False      # nothing to recycle at interpreter exit
     return arr
 
 
