@@ -283,3 +283,40 @@ def test_sfc_order_shrinks_the_interface_of_a_shuffled_mesh():
     part = partition.partition_mesh(P, Es, 1, 4, order="sfc")
     gl = part.node_map.numpy()
     assert np.array_equal(gl[part.elements.numpy()], Es[part.element_ids.numpy()])
+
+
+def test_leased_result_buffers_bookkeeping(monkeypatch):
+    """Host-result ownership (assembly._lease / _leased_array): at most _LEASE_MAX buffers per size are out, a buffer only goes
+    back to the free list when the array AND every view of it are gone, and it is then handed out again.  Page-locked allocation is
+    replaced by ordinary memory so that the logic runs without a GPU."""
+    import gc
+    import torch
+    from florence_b200 import assembly
+    real_empty = torch.empty
+    monkeypatch.setattr(assembly.torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "pin_memory"}))
+    assembly._lease_free.clear(); assembly._lease_out.clear()
+    t = torch.arange(1000, dtype=torch.float64)
+    held = []
+    for _ in range(assembly._LEASE_MAX):
+        buf, key = assembly._lease(t)
+        assert buf is not None
+        buf.copy_(t)
+        held.append(assembly._leased_array(buf, key))
+    assert assembly._lease(t)[0] is None                    # the limit: further results are pageable arrays
+    assert len({a.__array_interface__["data"][0] for a in held}) == assembly._LEASE_MAX
+    view = held[0][10:20]
+    addr = held[0].__array_interface__["data"][0]
+    del held[0]
+    gc.collect()
+    assert assembly._lease(t)[0] is None                    # a view still refers to the first buffer
+    assert np.array_equal(view, np.arange(10, 20, dtype=np.float64))
+    del view
+    gc.collect()
+    buf, key = assembly._lease(t)                           # ... now it is free again, and it is the same memory
+    assert buf is not None and buf.data_ptr() == addr
+    assembly._lease_return(key, buf)
+    del held
+    gc.collect()
+    assert assembly._lease_out[key] == 0 and len(assembly._lease_free[key]) == assembly._LEASE_MAX
+    assembly.release_host_buffers()
+    assert not assembly._lease_free
