@@ -518,9 +518,9 @@ def run_b200(args, rank, world, local_rank):
         # useful work of the regrouped algebra: Jacobian GEMM (3 ng x npe x 6) + traction GEMM (npe x 3 ng x 3), FMA = 2, + the
         # kinematics / material law per Gauss point; "executed" adds the padding of the 8x8x4 DMMA tiles (NE elements per batch)
         Fl_useful = 2.0 * (3 * ng) * npe * 6 + 2.0 * npe * (3 * ng) * 3 + ng * matfl
-        NE = 8 if p == 2 else 32
+        NE = 8 if p == 2 else 16
         t1 = ((3 * ng + 7) // 8) * ((npe + 3) // 4) * (6 * NE // 8)
-        t3 = ((npe + 7) // 8) * ((3 * ng + 3) // 4) * (3 * NE // 8)
+        t3 = ((npe + 7) // 8) * ((3 * ng + 3) // 4) * (3 * NE // 8) * (2 if p == 1 else 1)   # hex8: half the warps of the traction GEMM run an empty m-tile
         Fl_exec = (t1 + t3) / float(NE) * 512.0 + ng * matfl
         kname = "explicit_elements_mma_kernel<%s,%d,%d,%d>" % (matname, npe, ng, NE)
         out.update({"metric": "explicit DOF-updates/s", "value": ndof_global * nsteps / (ems * 1e-3), "unit": "DOF-updates/s",

@@ -16,6 +16,15 @@
 // buffer and reduced per node in ascending element order (deterministic; the reference's summation order).
 #include "fl_explicit_mma.cuh"
 
+// hex8 batch of the DMMA force kernel: elements per batch and warp split of the traction GEMM.  16 elements per batch need 42 kB of
+// shared memory per block, so four blocks (16 warps) fit an SM instead of two: 3.08 -> 2.79 ms per 8 M elements (the kernel is bound
+// by its own instruction latencies: issue 29 %, `wait` 2.6 per issue at 8 warps per SM).  Five or six blocks (96 / 80 registers) are
+// slower again (2.81 / 3.02 ms): profiles/hex8_explicit_bench.py.
+#ifndef FL_HEX8_NE
+#define FL_HEX8_NE 16
+#define FL_HEX8_WM3 2
+#endif
+
 namespace fl {
 
 constexpr int EXPL_THREADS = 256;
@@ -362,7 +371,7 @@ static int launch_expl(fl_handle* h, const double* Eulerx, const double* Eulerp,
     if constexpr (D == 3 && !EL) {
         // fixed shapes of the benchmark configs run the tensor-core (DMMA) formulation
         if (h->use_mma && npe == 27 && ng == 27) return launch_expl_mma<MAT, 27, 27, 8, 4, 4>(h, Eulerx, prm, te, st);
-        if (h->use_mma && npe == 8 && ng == 8) return launch_expl_mma<MAT, 8, 8, 32, 1, 1>(h, Eulerx, prm, te, st);
+        if (h->use_mma && npe == 8 && ng == 8) return launch_expl_mma<MAT, 8, 8, FL_HEX8_NE, 1, FL_HEX8_WM3>(h, Eulerx, prm, te, st);
     }
     const int per = npe > ng ? npe : ng;
     if (per > EXPL_THREADS) {

@@ -35,8 +35,11 @@ struct mma_shape {
     static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * XX_SZ + SCR_SZ + P_SZ);  // coordinates are double-buffered
 };
 
+#ifndef FL_HEX8_MINB
+#define FL_HEX8_MINB 4
+#endif
 template <int MAT, int NPE, int NG, int NE, int WM1, int WM3>
-__global__ void __launch_bounds__(MMA_THREADS, (NPE > 8 ? 3 : 4))
+__global__ void __launch_bounds__(MMA_THREADS, (NPE > 8 ? 3 : FL_HEX8_MINB))
 explicit_elements_mma_kernel(const int32_t* __restrict__ conn, const double* __restrict__ X, const double* __restrict__ x,
                              const double* __restrict__ jm, const double* __restrict__ gw, int64_t nelem, int ldg, MatParams prm,
                              double* __restrict__ te) {
