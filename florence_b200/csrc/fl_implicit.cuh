@@ -554,6 +554,11 @@ int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, co
         // forced (option value 2): its 27 -> 32 tile padding makes the generic kernel the faster one
         if (h->use_mma_implicit == 2 && h->npe == 27 && h->ng == 27) return launch_impl_mma<MAT, 27, 27, 21>(h, Eulerx, Eulerp, prm, update, ke, te, st);
         if (h->use_mma_implicit && h->npe == 64 && h->ng == 64) return launch_impl_mma<MAT, 64, 64, FL_IMMA_KC64>(h, Eulerx, Eulerp, prm, update, ke, te, st);
+        // p = 3 tetrahedra (tet20, the reference's 14-point rule): K = 42 -> one chunk of 12 k-steps, 20 -> 32 node padding.
+        // Default for the electro-mechanical models (82 944 elements, EM_108: 5.63 ms against 6.77 ms for the generic kernel); for
+        // mechanics the padding costs more than the tensor pipe gains (3.25 against 2.47 ms, NeoHookean): option value 2 only
+        if (h->use_mma_implicit && (mat_traits<MAT>::electro || h->use_mma_implicit == 2) && h->npe == 20 && h->ng == 14)
+            return launch_impl_mma<MAT, 20, 14, 12>(h, Eulerx, Eulerp, prm, update, ke, te, st);
     }
     if constexpr (D == 3 && MAT == MAT_LINEAR_ELASTIC) {
         // tet10 / hex8 (8 Gauss points): warp-autonomous kernel, no block barriers, no staging tile (fl_implicit_warp.cuh)

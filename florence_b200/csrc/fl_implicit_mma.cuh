@@ -1,4 +1,4 @@
-// fl_implicit_mma.cuh -- element stiffness of high-order hexahedra (p >= 2: hex27, hex64) on the fp64 tensor-core path.
+// fl_implicit_mma.cuh -- element stiffness of high-order elements (hex27, hex64, hex125 Poisson, tet20) on the fp64 tensor-core path.
 //
 // Same quantities as implicit_elements_kernel (fl_implicit.cuh; reference _LowLevelAssemblyDF_.h:69-131,
 // _LowLevelAssemblyDPF_.h:73-150, _ConstitutiveStiffnessDF_.h:83-156, _GeometricStiffness_.h:61-144), written in the
@@ -27,7 +27,9 @@ template <int NPE, int NG, int NV, int KC, int NTB_ = 0>
 struct imma_shape {
     static constexpr int C3 = 3 * NV;                       // rows/cols of Chat_g
     static constexpr int NPAIR = NV * (NV + 1) / 2;         // dof pairs i <= j that are contracted (K^{ji} is the mirror image)
-    static constexpr int MT = (NPE + 7) / 8, NT = (NPE + 7) / 8, KS = (3 * NG + 3) / 4;
+    // m8n8 tiles over the padded node count; an even number of them, so that every DMMA warp carries two m-tiles (tet20: 3 -> 4;
+    // the hexahedral shapes 27 / 64 / 125 already give 4 / 8 / 16)
+    static constexpr int MT = (((NPE + 7) / 8) + 1) & ~1, NT = MT, KS = (3 * NG + 3) / 4;
     static constexpr int NTB = NTB_ > 0 ? NTB_ : NT;        // n-tiles per column block: bounds the accumulators (MT/4 x NTB x 2 doubles
     static constexpr int NCB = NT / NTB;                    // per lane) when the element is wide (hex125: 16 n-tiles in 4 blocks)
     static_assert(NT % NTB == 0, "column blocks must tile the n-tiles");

@@ -540,12 +540,22 @@ static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cud
     auto kern = csr_gather_wide_kernel<NV, NPE_T>;
     FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    // a visit is NV*NV*npe doubles: 256 threads for the hexahedral shapes (243 .. 1024 per visit); elements with shorter visits
+    // (tet20: 180 / 320) run more, smaller blocks per SM
+    // (measured on 82 944 tet20, profiles/tet20_bench.py: nvar 3 2.53 -> 1.69 ms with 64 threads, nvar 4 3.23 -> 2.72 ms with 128;
+    // the register prefetch of the kernel covers 4 items per thread, so the block must keep 4 * threads >= visit length)
+    int threads = 256;
+    if (NPE_T == 0) {
+        const int run = NV * NV * h->npe;
+        threads = ((run + 3) / 4 + 63) / 64 * 64;
+        if (threads > 256) threads = 256;
+    }
+    FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) occ = 1;
     int64_t blocks = h->nnode;
     const int64_t cap = (int64_t)h->sm_count * occ * 8;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->npe, h->ke_plane_major, wmax,
+    kern<<<(unsigned)blocks, threads, smem, st>>>(h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->npe, h->ke_plane_major, wmax,
                                               h->max_adj, V);
     FL_CUDA_CHECK(cudaGetLastError());
     return FL_OK;
@@ -578,6 +588,8 @@ static int launch_csr_gather_T(fl_handle* h, const double* ke, double* V, cudaSt
 
 template <int NV>
 static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
+    // visits longer than 128 doubles: one block per node (tet20 measured both ways, profiles/tet20_bench.py: the warp-per-node
+    // row-buffer kernel below takes 3.12 ms (nvar 3) / 9.5 ms (nvar 4) where the block-per-node kernel takes 1.69 / 2.72 ms)
     if (NV * NV * h->npe > 128) {
         if (h->npe == 64) return launch_csr_gather_wide<NV, 64>(h, ke, V, st);
         if (h->npe == 27) return launch_csr_gather_wide<NV, 27>(h, ke, V, st);

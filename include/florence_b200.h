@@ -224,7 +224,7 @@ int fl_sfc_order(const double *points, const uint64_t *elements, int64_t nelem, 
                  int64_t *perm, void *stream);
 
 /* Tuning switches (for tests and A/B timing): option 0 = use the tensor-core (DMMA) explicit kernels for
- * hex8/hex27 (default 1); option 1 = use the DMMA implicit kernels for hex64 (default 1; 2 = also hex27; 3 = hex64 with
+ * hex8/hex27 (default 1); option 1 = use the DMMA implicit kernels for hex64 and electro-mechanical tet20 (default 1; 2 = also hex27 and mechanical tet20; 3 = hex64 with
  * the K_e scratch as dof-pair planes instead of per-row-node planes); option 2 = use the
  * warp-autonomous LinearElastic kernel: 1 = tet10 (default), 2 = tet10 and hex8, 0 = off; option 3 = CSR value reduction of the
  * element-order paths: 0 = shared-memory row-buffer kernels, 1 = register-resident slot-owner gather (nvar 2..4, low-order

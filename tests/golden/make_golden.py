@@ -224,6 +224,15 @@ def gen_assembly_hi(out):
     out["asm_cases"] = np.array([_asm_case(out, rng, *case) for case in cases])
 
 
+def gen_assembly_tet3(out):
+    """Cubic tetrahedra (tet20, 14 Gauss points): the p >= 3 simplex shape of BASELINE north_star ("high-order (p>=3) hex/tet").
+    Small meshes (6 and 12 elements) of the reference's own tet20 node arrangement and quadrature, mechanics and electro-mechanics."""
+    rng = np.random.default_rng(31)
+    cases = [("tet", 3, 1, "NeoHookean"), ("tet", 3, (2, 1, 1), "MooneyRivlin"), ("tet", 3, 1, "IsotropicElectroMechanics_108"),
+             ("tet", 3, 1, "LinearElastic")]
+    out["asm_cases"] = np.array([_asm_case(out, rng, *case) for case in cases])
+
+
 def gen_laplacian(out):
     names = []
     for etype, p, n in (("hex", 2, 2), ("hex", 4, 1), ("tet", 2, 2), ("quad", 2, 3), ("tri", 1, 3)):
@@ -401,7 +410,8 @@ def gen_explicit_rules(out):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "materials", "assembly", "laplacian", "explicit"]
-    gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, assembly_hi=gen_assembly_hi, laplacian=gen_laplacian,
+    gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, assembly_hi=gen_assembly_hi, assembly_tet3=gen_assembly_tet3,
+                laplacian=gen_laplacian,
                 explicit=gen_explicit, explicit_rules=gen_explicit_rules)
     for w in which:
         out = {}

@@ -17,19 +17,21 @@ pytestmark = pytest.mark.gpu
 
 ELEC = ["IsotropicElectroMechanics_101", "IsotropicElectroMechanics_105", "IsotropicElectroMechanics_108"]
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+GOLD_FILES = ("golden_assembly.npz", "golden_assembly_hi.npz", "golden_assembly_tet3.npz")   # tet3: cubic tetrahedra (tet20, 14 Gauss points)
 
 
 def _cases():
     out = []
-    for f in ("golden_assembly.npz", "golden_assembly_hi.npz"):
+    for f in GOLD_FILES:
         out += [str(s) for s in np.load(os.path.join(GOLD, f))["asm_cases"]]
     return out
 
 
 def _load(key):
-    g = np.load(os.path.join(GOLD, "golden_assembly.npz"))
-    if key + "_points" not in g.files:
-        g = np.load(os.path.join(GOLD, "golden_assembly_hi.npz"))
+    for f in GOLD_FILES:
+        g = np.load(os.path.join(GOLD, f))
+        if key + "_points" in g.files:
+            break
     names = ("points", "elements", "Eulerx", "Jm", "AllGauss", "Bases", "K_data", "K_indices", "K_indptr", "T", "update", "prm",
              "sp_indices", "sp_indptr")
     c = {n: g[key + "_" + n] for n in names}
@@ -311,9 +313,12 @@ def test_explicit_tensor_core_kernel_equals_scalar_kernel_and_oracle(p, n):
 
 
 @pytest.mark.parametrize("key", ["asm_hex2_n2_NeoHookean", "asm_hex3_n1_MooneyRivlin", "asm_hex2_n1_IsotropicElectroMechanics_108",
-                                 "asm_hex3_n1_IsotropicElectroMechanics_108", "asm_hex2_n1_NearlyIncompressibleMooneyRivlin"])
+                                 "asm_hex3_n1_IsotropicElectroMechanics_108", "asm_hex2_n1_NearlyIncompressibleMooneyRivlin",
+                                 "asm_tet3_n1_NeoHookean", "asm_tet3_n2x1x1_MooneyRivlin", "asm_tet3_n1_IsotropicElectroMechanics_108",
+                                 "asm_tet3_n1_LinearElastic"])
 def test_implicit_tensor_core_kernel_equals_generic_kernel(key):
-    """hex27 / hex64 run the DMMA parent-space formulation by default; the generic column-owner kernel must give the same K_e."""
+    """hex64 runs the DMMA parent-space formulation by default, hex27 and tet20 (20 -> 32 node padding) when option 1 is 2; the
+    generic column-owner kernel must give the same K_e, and both must match the reference's K."""
     from florence_b200 import backend
     from oracle import oracle as orc
     c = _load(key)
@@ -334,6 +339,16 @@ def test_implicit_tensor_core_kernel_equals_generic_kernel(key):
     K0 = csr_matrix((out[0][0], (out[0][2], out[0][3])), shape=(n, n))
     _blockwise_close(K1, K0, nvar, ndim, 1e-10)
     _vec_close(out[1][1], out[0][1], nvar, ndim, 1e-11)
+    Kref = csr_matrix((c["K_data"], c["K_indices"], c["K_indptr"]), shape=(n, n))
+    _blockwise_close(K1, Kref, nvar, ndim, 1e-10)
+    _vec_close(out[1][1], c["T"], nvar, ndim, 1e-11)
+    # CSR mode through the tensor-core kernel: the same matrix, deterministic
+    h.set_option(1, 2)
+    V1, _ = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, int(c["update"]), mode="csr")
+    V1b, _ = h.assemble_implicit(c["Eulerx"], c["Eulerp"], mat, form, int(c["update"]), mode="csr")
+    assert torch.equal(V1, V1b)
+    Kc = csr_matrix((V1.cpu().numpy(), c["sp_indices"], c["sp_indptr"]), shape=(n, n))
+    _blockwise_close(Kc, Kref, nvar, ndim, 1e-10)
     h.close()
 
 

@@ -81,7 +81,7 @@ def _case(g, key):
 def _asm_cases():
     import os
     out = []
-    for f in ("assembly", "assembly_hi"):
+    for f in ("assembly", "assembly_hi", "assembly_tet3"):
         d = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_%s.npz" % f))
         out += [(f, str(s)) for s in d["asm_cases"]]
     return out
