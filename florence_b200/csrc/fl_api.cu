@@ -167,6 +167,7 @@ int fl_set_option(fl_handle* h, int option, int value) {
     if (!h) { set_error("null handle"); return FL_ERR_INVALID; }
     if (option == 0) { h->use_mma = value ? 1 : 0; return FL_OK; }
     if (option == 1) { h->use_mma_implicit = value; return FL_OK; }
+    if (option == 5) { h->wide_unpipelined = value ? 1 : 0; return FL_OK; }
     if (option == 2) { h->use_warp_iso = value; return FL_OK; }
     if (option == 3) { h->use_reg_gather = value; return FL_OK; }
     if (option == 4) { h->use_stream = value; return FL_OK; }

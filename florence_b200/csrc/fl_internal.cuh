@@ -138,6 +138,7 @@ struct fl_handle {
                                  // 1 = dof-pair planes [(i,j)][a][b] (DMMA kernels: every fragment store fills whole sectors),
                                  // 2 = per-row-node planes [a][(i,j)][b] (same stores; one visit of the reduction is one contiguous run)
     int use_warp_iso = 1;        // implicit path: warp-autonomous LinearElastic kernel, 1 = tet10, 2 = tet10 + hex8 (fl_set_option 2)
+    int wide_unpipelined = 0;    // 1: hex64 / nvar 4 CSR reduction without the cross-node software pipeline (fl_set_option 5; A/B timing)
     int use_mma_implicit = 1;    // implicit path: DMMA kernels for hex64 / electro tet20; 2 = also hex27 / mechanics tet20 (fl_set_option 1)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

@@ -396,6 +396,15 @@ csr_gather_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict
     }
 }
 
+// Plane stride of the component-plane row buffer [(i,l)][rank]: the write-out reads rank r of plane l for consecutive CSR columns
+// c = r*NV + l, so the NV planes must start 16/NV banks (of 8 bytes) apart -- with the plain stride (64, 112, 343 neighbours ...)
+// the common hex64 node classes read with a 4-way bank conflict.
+template <int NV>
+__host__ __device__ __forceinline__ int plane_stride(int cn) {
+    constexpr int TARGET = NV == 4 ? 4 : (NV == 3 ? 5 : (NV == 2 ? 8 : 0));
+    return NV == 1 ? cn : cn + ((TARGET - cn) & 15);
+}
+
 // Wide rows (high-order elements: nvar*ndof > 128 doubles per visit): one block per node, the threads split each visit's run.
 template <int NV, int NPE_T>
 __global__ void __launch_bounds__(256)
@@ -414,10 +423,12 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
     uint16_t* rks = reinterpret_cast<uint16_t*>(flats + ((max_adj + 1) & ~1));
     for (int64_t n = blockIdx.x; n < nnode; n += gridDim.x) {
         const int w = (int)(nbr_ptr[n + 1] - nbr_ptr[n]) * NV;
+        int cnp = plane_stride<NV>(w / NV);           // plane-major modes: stride of a component plane of the row buffer
+        if (cnp * NV > wmax) cnp = w / NV;            // (the widest nodes when the padded stride would cost a block per SM)
         const int64_t k0 = adj_ptr[n];
         const int nvis = (int)(adj_ptr[n + 1] - k0);
         __syncthreads();
-        for (int t = threadIdx.x; t < NV * w; t += blockDim.x) rowbuf[t] = 0.0;
+        for (int t = threadIdx.x; t < (plane_major ? NV * NV * cnp : NV * w); t += blockDim.x) rowbuf[t] = 0.0;
         for (int t = threadIdx.x; t < nvis; t += blockDim.x) flats[t] = adj_idx[k0 + t];
         for (int t = threadIdx.x; t < nvis * npe; t += blockDim.x) rks[t] = rank_adj[k0 * npe + t];
         __syncthreads();
@@ -443,7 +454,7 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
                 // consecutive lanes hold consecutive column nodes b of one (i,l) plane: the row buffer is kept as component
                 // planes [(i,l)][rank] so that they land in distinct banks (rank*NV + l would be an NV*2-way conflict)
                 const int il = t / npe, b = t - il * npe;
-                return il * (w / NV) + (int)rk[b];
+                return il * cnp + (int)rk[b];
             }
             const int i = t / ndof, c = t - i * ndof;
             const int b = c / NV, l = c - b * NV;
@@ -454,7 +465,7 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
             // destinations of different warps never meet and the visits are ordered by __syncwarp alone -- no block barrier per visit
             // (ncu: 3.0 barrier stalls per issue with the items dealt round-robin over the block)
             const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-            const int cn = w / NV;
+            const int cn = cnp;
             int il[4], bb[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) { il[u] = 2 * wp + (u >> 1); bb[u] = ln + 32 * (u & 1); }
@@ -515,11 +526,16 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
         }
         const int64_t base = nbr_ptr[n] * NV * NV;
         if (plane_major) {
-            const int cn = w / NV;
-            for (int t = threadIdx.x; t < NV * w; t += blockDim.x) {
-                const int i = t / w, c = t - i * w;
-                const int r = c / NV, l = c - r * NV;
-                V[base + t] = rowbuf[(i * NV + l) * cn + r];
+            // row i of the node, CSR column c = r*NV + l  <-  plane (i,l), rank r.  No division by a run-time number: this loop was
+            // 43 % of the kernel's instructions when it decoded a flat index with `/ w` (ncu source page, prof_r2_hi)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double* Vi = V + base + (int64_t)i * w;
+                const double* rb = rowbuf + (i * NV) * cnp;
+                for (int c = threadIdx.x; c < w; c += blockDim.x) {
+                    const int r = c / NV, l = c - r * NV;
+                    Vi[c] = rb[l * cnp + r];
+                }
             }
         } else {
             for (int t = threadIdx.x; t < NV * w; t += blockDim.x) V[base + t] = rowbuf[t];
@@ -527,19 +543,162 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
     }
 }
 
+// hex64 with nvar 4 and a plane-major K_e scratch (config 4): the block-per-node reduction above, software-pipelined ACROSS nodes.
+// In the kernel above a node costs three dependent global round trips (row pointers -> connectivity index and rank rows of its
+// visits -> K_e values) with five blocks per SM to hide them: 2.9 ms for 24^3 elements, and the time did not move when 43 % of the
+// instructions were removed (division-free write-out), i.e. it is bound by that latency chain.  Here the row pointers of the node
+// after next travel to shared memory by cp.async, the visit lists of the next node wait in three registers per thread while the
+// current node is reduced, and the first visit of the next node is loaded before the current node's rows are written out.
+// Warp w owns the component planes 2w and 2w+1 of the row buffer outright (128 items per visit = 4 per lane): zeroing and the
+// visits of a node need __syncwarp only; two block barriers per node (row buffer complete / row buffer free).
+// Same sums in the same order as csr_gather_wide_kernel: bit-identical V.  Needs max_adj <= 8 (two rank entries per thread).
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+csr_gather_hex64_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
+                        const uint16_t* __restrict__ rank_adj, const double* __restrict__ ke, int64_t nnode, int plane_major, int wmax,
+                        double* __restrict__ V) {
+    constexpr int NV = 4, NPE = 64, MAXV = 8;
+    extern __shared__ double rowbuf[];                                          // [(i,l)][plane stride]
+    int64_t* ptrs = reinterpret_cast<int64_t*>(rowbuf + (size_t)NV * wmax);    // [3][adj_ptr n, n+1, nbr_ptr n, n+1]
+    int32_t* flats = reinterpret_cast<int32_t*>(ptrs + 12);                     // [MAXV]      flat connectivity index per visit
+    uint16_t* rks = reinterpret_cast<uint16_t*>(flats + MAXV);                 // [MAXV][64]  rank rows per visit
+    uint32_t* rks2 = reinterpret_cast<uint32_t*>(rks);
+    const int tid = threadIdx.x, wp = tid >> 5, ln = tid & 31;
+    const int64_t stride = gridDim.x;
+    auto issue_ptrs = [&](int64_t n, int slot) {
+        if (tid < 4 && n < nnode) cp_async_8(&ptrs[slot * 4 + tid], tid < 2 ? adj_ptr + n + tid : nbr_ptr + n + (tid - 2));
+    };
+    int il[4], bb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { il[u] = 2 * wp + (u >> 1); bb[u] = ln + 32 * (u & 1); }
+    auto src = [&](int32_t flat, int u) -> int64_t {
+        const int64_t e = flat >> 6;
+        const int a = flat & 63;
+        return plane_major == 2 ? e * (int64_t)(256 * 256) + ((int64_t)a * 16 + il[u]) * 64 + bb[u]
+                                : e * (int64_t)(256 * 256) + ((int64_t)il[u] * 64 + a) * 64 + bb[u];
+    };
+    int64_t n = blockIdx.x;
+    issue_ptrs(n, 0);
+    issue_ptrs(n + stride, 1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    double nxt[4] = {0.0, 0.0, 0.0, 0.0};
+    if (n < nnode) {
+        const int64_t k0 = ptrs[0];
+        const int nvis = (int)(ptrs[1] - k0);
+        if (tid < nvis) flats[tid] = adj_idx[k0 + tid];
+        if (2 * tid < nvis * NPE) rks2[tid] = *reinterpret_cast<const uint32_t*>(rank_adj + k0 * NPE + 2 * tid);
+        if (nvis > 0) {
+            const int32_t f = adj_idx[k0];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nxt[u] = ke[src(f, u)];
+        }
+    }
+    __syncthreads();
+    for (int j = 0; n < nnode; ++j, n += stride) {
+        const int slot = j % 3, slot1 = (j + 1) % 3;
+        issue_ptrs(n + 2 * stride, (j + 2) % 3);
+        // the next node's visit lists: plain loads into registers, first used after this node's visits
+        uint32_t rkn = 0;
+        int32_t fln = 0, f0n = 0;
+        int nvis1 = 0;
+        if (n + stride < nnode) {
+            const int64_t k1 = ptrs[slot1 * 4];
+            nvis1 = (int)(ptrs[slot1 * 4 + 1] - k1);
+            if (tid < nvis1) fln = adj_idx[k1 + tid];
+            if (2 * tid < nvis1 * NPE) rkn = *reinterpret_cast<const uint32_t*>(rank_adj + k1 * NPE + 2 * tid);
+            if (nvis1 > 0) f0n = adj_idx[k1];
+        }
+        const int64_t k0 = ptrs[slot * 4], nb0 = ptrs[slot * 4 + 2];
+        const int nvis = (int)(ptrs[slot * 4 + 1] - k0);
+        const int cn = (int)(ptrs[slot * 4 + 3] - nb0);
+        const int w = cn * NV;
+        int cnp = plane_stride<NV>(cn);
+        if (cnp * NV > wmax) cnp = cn;                      // the widest nodes when the padded stride would cost a block per SM
+        double* mine = rowbuf + 2 * wp * cnp;               // planes 2 wp and 2 wp + 1
+        for (int t = ln; t < 2 * cnp; t += 32) mine[t] = 0.0;
+        __syncwarp();
+        for (int v = 0; v < nvis; ++v) {
+            double cur[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+            if (v + 1 < nvis) {
+                const int32_t f = flats[v + 1];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nxt[u] = ke[src(f, u)];
+            }
+            const uint16_t* rk = rks + v * NPE;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rowbuf[il[u] * cnp + (int)rk[bb[u]]] += cur[u];
+            __syncwarp();
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();                                    // row buffer complete, visit lists no longer read, row pointers landed
+        if (tid < nvis1) flats[tid] = fln;
+        if (2 * tid < nvis1 * NPE) rks2[tid] = rkn;
+        if (nvis1 > 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nxt[u] = ke[src(f0n, u)];
+        }
+        const int64_t base = nb0 * NV * NV;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double* Vi = V + base + (int64_t)i * w;
+            const double* rb = rowbuf + (i * NV) * cnp;
+            for (int c = tid; c < w; c += 256) Vi[c] = rb[(c & 3) * cnp + (c >> 2)];
+        }
+        __syncthreads();                                    // row buffer free, next visit lists visible
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 template <int NV, int NPE_T>
 static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cudaStream_t st) {
     const Pattern& p = h->pat;
-    const int wmax = p.max_cnt * NV;
-    const size_t smem = sizeof(double) * NV * (size_t)wmax + sizeof(int32_t) * ((h->max_adj + 1) & ~1) +
+    // row buffer of the widest node: NV rows of max_cnt*NV entries, or NV*NV component planes of the padded stride
+    int wmax = (h->ke_plane_major ? plane_stride<NV>(p.max_cnt) : p.max_cnt) * NV;
+    size_t smem = sizeof(double) * NV * (size_t)wmax + sizeof(int32_t) * ((h->max_adj + 1) & ~1) +
                         ((sizeof(uint16_t) * (size_t)h->max_adj * h->npe + 7) & ~(size_t)7);
     if (smem > (size_t)h->max_smem_optin) {
         set_error("CSR rows of %d entries do not fit shared memory", p.max_cnt * NV);
         return FL_ERR_UNSUPPORTED;
     }
+    if (NV == 4 && NPE_T == 64 && h->ke_plane_major && !h->wide_unpipelined && h->max_adj <= 8) {
+        const size_t meta = 12 * sizeof(int64_t) + 8 * sizeof(int32_t) + 8 * 64 * sizeof(uint16_t);
+        auto occ_of = [&](int wm, int* occ) {
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, csr_gather_hex64_kernel, 256, sizeof(double) * NV * (size_t)wm + meta);
+        };
+        // the conflict-free plane stride for every node if that costs no block per SM, else for all but the widest nodes
+        int wm = wmax, occ_pad = 0, occ_raw = 0;
+        FL_CUDA_CHECK(cudaFuncSetAttribute(csr_gather_hex64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(double) * NV * (size_t)wmax + meta)));
+        FL_CUDA_CHECK(occ_of(wmax, &occ_pad));
+        FL_CUDA_CHECK(occ_of(p.max_cnt * NV, &occ_raw));
+        if (occ_raw > occ_pad) wm = p.max_cnt * NV;
+        const int occ2 = occ_raw > occ_pad ? occ_raw : occ_pad;
+        if (occ2 >= 1) {
+            // persistent blocks: each walks nodes b, b + grid, ... so that its prefetches always have a next node
+            int64_t blocks = (int64_t)h->sm_count * occ2;
+            if (blocks > h->nnode) blocks = h->nnode;
+            csr_gather_hex64_kernel<<<(unsigned)blocks, 256, sizeof(double) * NV * (size_t)wm + meta, st>>>(
+                h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->ke_plane_major, wm, V);
+            FL_CUDA_CHECK(cudaGetLastError());
+            return FL_OK;
+        }
+    }
     auto kern = csr_gather_wide_kernel<NV, NPE_T>;
     FL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
+    if (h->ke_plane_major) {   // padded plane stride only where it does not cost a block per SM
+        const size_t raw = smem - sizeof(double) * NV * (size_t)(wmax - p.max_cnt * NV);
+        int o_pad = 0, o_raw = 0;
+        FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o_pad, kern, 256, smem));
+        FL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o_raw, kern, 256, raw));
+        if (o_raw > o_pad) { wmax = p.max_cnt * NV; smem = raw; }
+    }
     // a visit is NV*NV*npe doubles: 256 threads for the hexahedral shapes (243 .. 1024 per visit); elements with shorter visits
     // (tet20: 180 / 320) run more, smaller blocks per SM
     // (measured on 82 944 tet20, profiles/tet20_bench.py: nvar 3 2.53 -> 1.69 ms with 64 threads, nvar 4 3.23 -> 2.72 ms with 128;

@@ -231,7 +231,8 @@ int fl_sfc_order(const double *points, const uint64_t *elements, int64_t nelem, 
  * elements whose K_e row blocks are multiples of 16 bytes), 2 = whichever was measured faster for the shape (default: the gather for
  * 2-D elements, hex8 mechanics and tet10 electro-mechanics); option 4 = tet10 mechanics (any material; hex8 LinearElastic when option 2 is 2) in CSR
  * mode: 1 = K_e stored along a space-filling curve and reduced in completion order (default), 2 = the same with the element kernel
- * and the reduction running concurrently on two streams (measured slower), 3 = the kernels of 2 one after the other, 0 = off. */
+ * and the reduction running concurrently on two streams (measured slower), 3 = the kernels of 2 one after the other, 0 = off;
+ * option 5 = 1: hex64 / nvar 4 CSR reduction without the cross-node software pipeline (A/B timing; default 0). */
 int fl_set_option(fl_handle *h, int option, int value);
 
 /* Per-kernel device timing of the most recent fl_assemble_* call (CUDA events recorded on the call's stream):

@@ -15,6 +15,8 @@ mu = 5e4
 mat = backend.make_material(8, 1200.0, mu1=mu, mu2=mu, lamb=2 * mu * 0.4 / (1 - 0.8), eps_2=4 * 8.8541e-12)
 if os.environ.get('FL_OPT1'):
     h.set_option(1, int(os.environ['FL_OPT1']))   # 3: K_e scratch as dof-pair planes (round-2 layout before the per-row-node planes)
+if os.environ.get('FL_OPT5'):
+    h.set_option(5, int(os.environ['FL_OPT5']))   # 1: CSR reduction without the cross-node software pipeline
 nnz = h.build_pattern(4)
 V = torch.empty(nnz, dtype=torch.float64, device=dev); T = torch.empty(pts.shape[0] * 4, dtype=torch.float64, device=dev)
 h.set_timing(True)
