@@ -549,18 +549,30 @@ csr_gather_wide_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __res
 // instructions were removed (division-free write-out), i.e. it is bound by that latency chain.  Here the row pointers of the node
 // after next travel to shared memory by cp.async, the visit lists of the next node wait in three registers per thread while the
 // current node is reduced, and the first visit of the next node is loaded before the current node's rows are written out.
-// Warp w owns the component planes 2w and 2w+1 of the row buffer outright (128 items per visit = 4 per lane): zeroing and the
+// A warp owns its component planes of the row buffer outright (nvar 4: planes 2w and 2w+1, 4 items per lane and visit): zeroing and the
 // visits of a node need __syncwarp only; two block barriers per node (row buffer complete / row buffer free).
 // Same sums in the same order as csr_gather_wide_kernel: bit-identical V.  Needs max_adj <= 8 (two rank entries per thread).
+// nvar 4 (config 4): 8 warps x 2 planes; nvar 3 (mechanics on hex64): 9 warps x 1 plane.
 __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+template <int NV>
+struct hex64_gather_cfg {
+    static constexpr int PPW = NV == 4 ? 2 : 1;                 // component planes per warp
+    static constexpr int NW = (NV * NV + PPW - 1) / PPW;        // nvar 4: 8 warps x 2 planes, nvar 3: 9 warps x 1 plane
+    static constexpr int THREADS = NW * 32, IPL = 2 * PPW;      // items per lane and visit (a plane row is 64 doubles = 2 per lane)
+    static constexpr int MAXV = 8;                              // visits whose rank rows fit two entries per thread
+    static constexpr size_t META = 12 * sizeof(int64_t) + MAXV * sizeof(int32_t) + MAXV * 64 * sizeof(uint16_t);
+};
+
+template <int NV>
+__global__ void __launch_bounds__(hex64_gather_cfg<NV>::THREADS)
 csr_gather_hex64_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, const int64_t* __restrict__ nbr_ptr,
                         const uint16_t* __restrict__ rank_adj, const double* __restrict__ ke, int64_t nnode, int plane_major, int wmax,
                         double* __restrict__ V) {
-    constexpr int NV = 4, NPE = 64, MAXV = 8;
+    using C = hex64_gather_cfg<NV>;
+    constexpr int NPE = 64, MAXV = C::MAXV, PPW = C::PPW, IPL = C::IPL, NT = C::THREADS, NDOF = NV * NPE;
     extern __shared__ double rowbuf[];                                          // [(i,l)][plane stride]
     int64_t* ptrs = reinterpret_cast<int64_t*>(rowbuf + (size_t)NV * wmax);    // [3][adj_ptr n, n+1, nbr_ptr n, n+1]
     int32_t* flats = reinterpret_cast<int32_t*>(ptrs + 12);                     // [MAXV]      flat connectivity index per visit
@@ -571,21 +583,23 @@ csr_gather_hex64_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __re
     auto issue_ptrs = [&](int64_t n, int slot) {
         if (tid < 4 && n < nnode) cp_async_8(&ptrs[slot * 4 + tid], tid < 2 ? adj_ptr + n + tid : nbr_ptr + n + (tid - 2));
     };
-    int il[4], bb[4];
+    int il[IPL], bb[IPL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { il[u] = 2 * wp + (u >> 1); bb[u] = ln + 32 * (u & 1); }
+    for (int u = 0; u < IPL; ++u) { il[u] = PPW * wp + (u >> 1); bb[u] = ln + 32 * (u & 1); }
     auto src = [&](int32_t flat, int u) -> int64_t {
         const int64_t e = flat >> 6;
         const int a = flat & 63;
-        return plane_major == 2 ? e * (int64_t)(256 * 256) + ((int64_t)a * 16 + il[u]) * 64 + bb[u]
-                                : e * (int64_t)(256 * 256) + ((int64_t)il[u] * 64 + a) * 64 + bb[u];
+        return plane_major == 2 ? e * (int64_t)(NDOF * NDOF) + ((int64_t)a * (NV * NV) + il[u]) * 64 + bb[u]
+                                : e * (int64_t)(NDOF * NDOF) + ((int64_t)il[u] * 64 + a) * 64 + bb[u];
     };
     int64_t n = blockIdx.x;
     issue_ptrs(n, 0);
     issue_ptrs(n + stride, 1);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    double nxt[4] = {0.0, 0.0, 0.0, 0.0};
+    double nxt[IPL];
+#pragma unroll
+    for (int u = 0; u < IPL; ++u) nxt[u] = 0.0;
     if (n < nnode) {
         const int64_t k0 = ptrs[0];
         const int nvis = (int)(ptrs[1] - k0);
@@ -594,7 +608,7 @@ csr_gather_hex64_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __re
         if (nvis > 0) {
             const int32_t f = adj_idx[k0];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nxt[u] = ke[src(f, u)];
+            for (int u = 0; u < IPL; ++u) nxt[u] = ke[src(f, u)];
         }
     }
     __syncthreads();
@@ -618,21 +632,21 @@ csr_gather_hex64_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __re
         const int w = cn * NV;
         int cnp = plane_stride<NV>(cn);
         if (cnp * NV > wmax) cnp = cn;                      // the widest nodes when the padded stride would cost a block per SM
-        double* mine = rowbuf + 2 * wp * cnp;               // planes 2 wp and 2 wp + 1
-        for (int t = ln; t < 2 * cnp; t += 32) mine[t] = 0.0;
+        double* mine = rowbuf + PPW * wp * cnp;             // this warp's component planes
+        for (int t = ln; t < PPW * cnp; t += 32) mine[t] = 0.0;
         __syncwarp();
         for (int v = 0; v < nvis; ++v) {
-            double cur[4];
+            double cur[IPL];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+            for (int u = 0; u < IPL; ++u) cur[u] = nxt[u];
             if (v + 1 < nvis) {
                 const int32_t f = flats[v + 1];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) nxt[u] = ke[src(f, u)];
+                for (int u = 0; u < IPL; ++u) nxt[u] = ke[src(f, u)];
             }
             const uint16_t* rk = rks + v * NPE;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) rowbuf[il[u] * cnp + (int)rk[bb[u]]] += cur[u];
+            for (int u = 0; u < IPL; ++u) rowbuf[il[u] * cnp + (int)rk[bb[u]]] += cur[u];
             __syncwarp();
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -641,14 +655,17 @@ csr_gather_hex64_kernel(const int64_t* __restrict__ adj_ptr, const int32_t* __re
         if (2 * tid < nvis1 * NPE) rks2[tid] = rkn;
         if (nvis1 > 0) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nxt[u] = ke[src(f0n, u)];
+            for (int u = 0; u < IPL; ++u) nxt[u] = ke[src(f0n, u)];
         }
         const int64_t base = nb0 * NV * NV;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             double* Vi = V + base + (int64_t)i * w;
             const double* rb = rowbuf + (i * NV) * cnp;
-            for (int c = tid; c < w; c += 256) Vi[c] = rb[(c & 3) * cnp + (c >> 2)];
+            for (int c = tid; c < w; c += NT) {
+                const int r = c / NV, l = c - r * NV;
+                Vi[c] = rb[l * cnp + r];
+            }
         }
         __syncthreads();                                    // row buffer free, next visit lists visible
     }
@@ -666,27 +683,31 @@ static int launch_csr_gather_wide(fl_handle* h, const double* ke, double* V, cud
         set_error("CSR rows of %d entries do not fit shared memory", p.max_cnt * NV);
         return FL_ERR_UNSUPPORTED;
     }
-    if (NV == 4 && NPE_T == 64 && h->ke_plane_major && !h->wide_unpipelined && h->max_adj <= 8) {
-        const size_t meta = 12 * sizeof(int64_t) + 8 * sizeof(int32_t) + 8 * 64 * sizeof(uint16_t);
-        auto occ_of = [&](int wm, int* occ) {
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, csr_gather_hex64_kernel, 256, sizeof(double) * NV * (size_t)wm + meta);
-        };
-        // the conflict-free plane stride for every node if that costs no block per SM, else for all but the widest nodes
-        int wm = wmax, occ_pad = 0, occ_raw = 0;
-        FL_CUDA_CHECK(cudaFuncSetAttribute(csr_gather_hex64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(sizeof(double) * NV * (size_t)wmax + meta)));
-        FL_CUDA_CHECK(occ_of(wmax, &occ_pad));
-        FL_CUDA_CHECK(occ_of(p.max_cnt * NV, &occ_raw));
-        if (occ_raw > occ_pad) wm = p.max_cnt * NV;
-        const int occ2 = occ_raw > occ_pad ? occ_raw : occ_pad;
-        if (occ2 >= 1) {
-            // persistent blocks: each walks nodes b, b + grid, ... so that its prefetches always have a next node
-            int64_t blocks = (int64_t)h->sm_count * occ2;
-            if (blocks > h->nnode) blocks = h->nnode;
-            csr_gather_hex64_kernel<<<(unsigned)blocks, 256, sizeof(double) * NV * (size_t)wm + meta, st>>>(
-                h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->ke_plane_major, wm, V);
-            FL_CUDA_CHECK(cudaGetLastError());
-            return FL_OK;
+    if constexpr ((NV == 3 || NV == 4) && NPE_T == 64) {
+        using C = hex64_gather_cfg<NV>;
+        constexpr size_t meta = C::META;
+        auto k64 = csr_gather_hex64_kernel<NV>;
+        if (h->ke_plane_major && !h->wide_unpipelined && h->max_adj <= C::MAXV &&
+            sizeof(double) * NV * (size_t)wmax + meta <= (size_t)h->max_smem_optin) {
+            auto occ_of = [&](int wm, int* occ) {
+                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k64, C::THREADS, sizeof(double) * NV * (size_t)wm + meta);
+            };
+            // the conflict-free plane stride for every node if that costs no block per SM, else for all but the widest nodes
+            int wm = wmax, occ_pad = 0, occ_raw = 0;
+            FL_CUDA_CHECK(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * NV * (size_t)wmax + meta)));
+            FL_CUDA_CHECK(occ_of(wmax, &occ_pad));
+            FL_CUDA_CHECK(occ_of(p.max_cnt * NV, &occ_raw));
+            if (occ_raw > occ_pad) wm = p.max_cnt * NV;
+            const int occ2 = occ_raw > occ_pad ? occ_raw : occ_pad;
+            if (occ2 >= 1) {
+                // persistent blocks: each walks nodes b, b + grid, ... so that its prefetches always have a next node
+                int64_t blocks = (int64_t)h->sm_count * occ2;
+                if (blocks > h->nnode) blocks = h->nnode;
+                k64<<<(unsigned)blocks, C::THREADS, sizeof(double) * NV * (size_t)wm + meta, st>>>(
+                    h->adj_ptr, h->adj_idx, p.nbr_ptr, p.rank_adj, ke, h->nnode, h->ke_plane_major, wm, V);
+                FL_CUDA_CHECK(cudaGetLastError());
+                return FL_OK;
+            }
         }
     }
     auto kern = csr_gather_wide_kernel<NV, NPE_T>;

@@ -398,10 +398,12 @@ def test_hex64_multi_element_against_oracle(matname, shape):
     h.close()
 
 
-def test_hex64_pipelined_reduction_is_bit_identical():
-    """The cross-node software-pipelined CSR reduction of hex64 / nvar 4 (csr_gather_hex64_kernel) adds the same visits in the same
-    order as the block-per-node kernel it replaces (option 5 = 1): V must not differ in a single bit, on a mesh with every node class
-    (vertex nodes with 8 visits down to interior nodes with one) and for both plane-major scratch layouts."""
+@pytest.mark.parametrize("electro", [True, False])
+def test_hex64_pipelined_reduction_is_bit_identical(electro):
+    """The cross-node software-pipelined CSR reduction of hex64 (csr_gather_hex64_kernel: nvar 4 electro-mechanics, nvar 3
+    mechanics) adds the same visits in the same order as the block-per-node kernel it replaces (option 5 = 1): V must not differ
+    in a single bit, on a mesh with every node class (vertex nodes with 8 visits down to interior nodes with one) and for both
+    plane-major scratch layouts."""
     from florence_b200 import backend, mesh as flmesh
     pts, els = flmesh.box_hex_mesh(3, 3, 2, p=3)
     Bases, Jm, AG = flmesh.tables("hex", 3)
@@ -410,13 +412,15 @@ def test_hex64_pipelined_reduction_is_bit_identical():
     phi = 9e3 * pts[:, 2] + 10.0 * (2 * torch.rand(pts.shape[0], dtype=torch.float64, generator=gen) - 1)
     h = backend.AssemblyHandle(pts, els, Jm, AG, Bases)
     mu = 5e4
-    mat = backend.make_material(8, 1200.0, mu1=mu, mu2=mu, lamb=2 * mu * 0.4 / (1 - 0.8), eps_2=4 * 8.8541e-12)
+    mat = backend.make_material(8 if electro else 2, 1200.0, mu1=mu, mu2=mu, lamb=2 * mu * 0.4 / (1 - 0.8), eps_2=4 * 8.8541e-12)
+    if not electro:
+        phi = None
     out = {}
     for layout in (1, 3):                      # per-row-node planes (default) / dof-pair planes
         h.set_option(1, layout)
         for unpipelined in (0, 1):
             h.set_option(5, unpipelined)
-            V, T = h.assemble_implicit(x, phi, mat, 1, True, mode="csr")
+            V, T = h.assemble_implicit(x, phi, mat, 1 if electro else 0, True, mode="csr")
             out[(layout, unpipelined)] = V.clone()
         assert torch.equal(out[(layout, 0)], out[(layout, 1)])
     assert torch.equal(out[(1, 0)], out[(3, 0)])
