@@ -780,8 +780,13 @@ static int launch_csr_gather_NV(fl_handle* h, const double* ke, double* V, cudaS
         case 8: return launch_csr_gather_T<NV, 8>(h, ke, V, st);
         case 10: return launch_csr_gather_T<NV, 10>(h, ke, V, st);
         case 27: return launch_csr_gather_T<NV, 27>(h, ke, V, st);
-        default: return launch_csr_gather_T<NV, 0>(h, ke, V, st);
+        // Poisson on p = 3 / p = 4 hexahedra (config 1): a visit is one row of 64 / 125 doubles; compile-time node counts turn the
+        // index decoding (64-bit `flat / npe`, `t / ndof`) into multiplies
+        case 64: if constexpr (NV == 1) return launch_csr_gather_T<NV, 64>(h, ke, V, st); else break;
+        case 125: if constexpr (NV == 1) return launch_csr_gather_T<NV, 125>(h, ke, V, st); else break;
+        default: break;
     }
+    return launch_csr_gather_T<NV, 0>(h, ke, V, st);
 }
 
 int launch_csr_gather(fl_handle* h, int nvar, const double* ke, double* V, cudaStream_t st) {
