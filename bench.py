@@ -594,8 +594,10 @@ def run_b200(args, rank, world, local_rank):
         dmma = backend.measure_fp64_peak(True, 20000)
         launches += 4
         nel4 = e4.shape[0]
-        # executed tensor-core work: 10 dof pairs (i <= j) x (8x8 tiles) x 48 k-steps DMMAs of 256 FMAs per element
-        fl_exec = 10 * 8 * 8 * 48 * 512.0
+        # executed tensor-core work per element: 6 off-diagonal dof pairs (i < j) x 64 tiles + 4 diagonal pairs x 36 upper-triangular
+        # tiles (the mirror tiles of a symmetric K^{ii} are skipped), x 48 k-steps, DMMAs of 256 FMAs
+        fl_exec = (6 * 64 + 4 * 36) * 48 * 512.0
+        fl_ref = 64 * (2 * 81 * 256 + 2 * 9 * 65536 + 2 * 65536 + 25 * 4096)   # SURVEY.md 8(d) implicit term, reference-algorithm count
         line["hiorder"] = {"metric": "elements assembled/s (K+residual, fp64)", "value": nel4 * world / (hms * 1e-3), "unit": "elements/s",
                            "ms_per_step": hms,
                            "config": {"workload": "hex64 (p=3) IsotropicElectroMechanics_108 Newton-step K(CSR)+T, %d^3 elements per GPU" % n4,
@@ -603,8 +605,11 @@ def run_b200(args, rank, world, local_rank):
                            "roofline": {"bound": "tensor", "achieved": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
                                         "frac": fl_exec * nel4 / (t4[0] * 1e-3) / 1e12 / dmma,
                                         "frac_whole_step": fl_exec * nel4 / (hms * 1e-3) / 1e12 / dmma,
-                                        "kernel": "implicit_elements_mma_kernel<EM_108,64,64,6>",
-                                        "kernel_ms": t4[0], "csr_gather_wide_ms": t4[1],
+                                        "kernel": "implicit_mma_prologue_kernel<EM_108,64,64> + implicit_mma_gemm_kernel<4,64,64,12,0>",
+                                        "kernel_ms": t4[0], "csr_reduction_kernel": "csr_gather_hex64_kernel<4>", "csr_reduction_ms": t4[1],
+                                        "reference_count": {"flops_per_element": fl_ref,
+                                                            "equivalent_tflops_whole_step": fl_ref * nel4 / (hms * 1e-3) / 1e12,
+                                                            "note": "what the reference's dense dgemm formulation would execute for the same K (SURVEY.md 8d)"},
                                         "peak_source": "builder-measured in this run (fl_measure_fp64_peak, mma.sync.m8n8k4.f64 loop); "
                                                        "MEASURED_PEAKS.json has no fp64 entry",
                                         "flops_per_element_executed_on_tensor_cores": fl_exec}}
