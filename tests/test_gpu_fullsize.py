@@ -65,6 +65,11 @@ def test_config2_tet10_linear_elastic_1M_elements():
     lhs = float((w[I.long()] * Vc * z[J.long()]).sum())
     rhs = float(w @ (K @ z))
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+    # ... and row by row: K z from the CSR values against the same product accumulated from the 898 M COO triplets
+    Kz = K @ z
+    Kz_coo = torch.zeros(nrow, dtype=torch.float64, device=dev).index_add_(0, I.long(), Vc * z[J.long()])
+    assert float((Kz - Kz_coo).abs().max()) <= 1e-10 * float(Kz.abs().max())
+    del Kz, Kz_coo
     # a random sample of element matrices against the oracle (COO layout is element-major)
     rng = np.random.default_rng(0)
     sample = np.sort(rng.choice(els.shape[0], 64, replace=False))
