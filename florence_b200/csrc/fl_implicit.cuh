@@ -555,8 +555,8 @@ int launch_impl_mat(fl_handle* h, const double* Eulerx, const double* Eulerp, co
         if (h->use_mma_implicit == 2 && h->npe == 27 && h->ng == 27) return launch_impl_mma<MAT, 27, 27, 21>(h, Eulerx, Eulerp, prm, update, ke, te, st);
         if (h->use_mma_implicit && h->npe == 64 && h->ng == 64) return launch_impl_mma<MAT, 64, 64, FL_IMMA_KC64>(h, Eulerx, Eulerp, prm, update, ke, te, st);
         // p = 3 tetrahedra (tet20, the reference's 14-point rule): K = 42 -> one chunk of 12 k-steps, 20 -> 32 node padding.
-        // Default for the electro-mechanical models (82 944 elements, EM_108: 5.63 ms against 6.77 ms for the generic kernel); for
-        // mechanics the padding costs more than the tensor pipe gains (3.25 against 2.47 ms, NeoHookean): option value 2 only
+        // Default for the electro-mechanical models (82 944 elements, EM_108: 5.08 ms against 6.76 ms for the generic kernel); for
+        // mechanics the padding costs more than the tensor pipe gains (2.85 against 2.47 ms, NeoHookean): option value 2 only
         if (h->use_mma_implicit && (mat_traits<MAT>::electro || h->use_mma_implicit == 2) && h->npe == 20 && h->ng == 14)
             return launch_impl_mma<MAT, 20, 14, 12>(h, Eulerx, Eulerp, prm, update, ke, te, st);
     }

@@ -213,8 +213,9 @@ implicit_mma_prologue_kernel(const int32_t* __restrict__ conn, const double* __r
 #ifndef FL_IMMA_KC64
 #define FL_IMMA_KC64 12   // K chunk of 12 k-steps: 52 KB of W double buffer + 46 KB of Chat per block, two blocks per SM, 40 barriers per element
 #endif
+// small elements (tet20, hex27: 4 x 4 tiles, 34-60 KB of shared memory per block) hold few accumulators: three blocks per SM
 template <int NV, int NPE, int NG, int KC, int NTB>
-__global__ void __launch_bounds__(IMMA_THREADS, FL_IMMA_MINB)
+__global__ void __launch_bounds__(IMMA_THREADS, (NPE <= 32 ? 3 : FL_IMMA_MINB))
 implicit_mma_gemm_kernel(const double* __restrict__ jmT, const double* __restrict__ chg, int64_t nelem, double* __restrict__ ke,
                          int plane_major, int sym_diag) {
     using S = imma_shape<NPE, NG, NV, KC, NTB>;
