@@ -233,6 +233,43 @@ def gen_assembly_tet3(out):
     out["asm_cases"] = np.array([_asm_case(out, rng, *case) for case in cases])
 
 
+def gen_mass(out):
+    """Consistent mass matrix from the reference's Python path (Assemble with analysis_type="dynamic", optimise=False):
+    M = sum_e sum_g rho N N^T w |det J_X| on every displacement dof (DisplacementFormulation.GetLocalMass), zero rows for the
+    potential dof of the electro-mechanical formulation.  Pins the consistent branch of __TotalConstantMassIntegrand__, which the
+    explicit fixtures (lumped M only) do not reach."""
+    from Florence.FiniteElements.Assembly import Assemble
+    names = []
+    for etype, p, n, matname in (("hex", 2, 2, "NeoHookean"), ("tet", 2, 2, "NeoHookean"), ("quad", 2, 3, "NeoHookean"),
+                                 ("hex", 1, 2, "IsotropicElectroMechanics_101"), ("tet", 3, 1, "NeoHookean")):
+        mesh = make_mesh(etype, p, n)
+        ndim = mesh.points.shape[1]
+        material, prm = material_of(matname, ndim)
+        material.has_low_level_dispatcher = False
+        electro = matname in ELEC
+        form = DisplacementPotentialFormulation(mesh) if electro else DisplacementFormulation(mesh)
+        fem_solver = FEMSolver(analysis_type="dynamic", analysis_subtype="implicit", mass_type="consistent", optimise=False,
+                               analysis_nature="nonlinear")
+        fem_solver.is_mass_computed = False
+        fs = form.function_spaces[0]
+        K, T, F, M = Assemble(fem_solver, fs, form, mesh, material, mesh.points.copy(), np.zeros(mesh.points.shape[0]))
+        M = M.tocsr(); M.sum_duplicates(); M.sort_indices()
+        key = "mass_%s%d_n%d_%s" % (etype, p, n, matname)
+        out[key + "_points"] = mesh.points
+        out[key + "_elements"] = mesh.elements.astype(np.int64)
+        out[key + "_Jm"] = fs.Jm
+        out[key + "_AllGauss"] = fs.AllGauss
+        out[key + "_Bases"] = fs.Bases
+        out[key + "_rho"] = np.array(float(material.rho))
+        out[key + "_nvar"] = np.array(int(form.nvar))
+        out[key + "_M_data"] = M.data
+        out[key + "_M_indices"] = M.indices
+        out[key + "_M_indptr"] = M.indptr
+        names.append(key)
+        print(key, M.shape, M.nnz, "sum", M.sum())
+    out["mass_cases"] = np.array(names)
+
+
 def gen_laplacian(out):
     names = []
     for etype, p, n in (("hex", 2, 2), ("hex", 4, 1), ("tet", 2, 2), ("quad", 2, 3), ("tri", 1, 3)):
@@ -410,7 +447,7 @@ def gen_explicit_rules(out):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tables", "materials", "assembly", "laplacian", "explicit"]
-    gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, assembly_hi=gen_assembly_hi, assembly_tet3=gen_assembly_tet3,
+    gens = dict(tables=gen_tables, materials=gen_materials, assembly=gen_assembly, assembly_hi=gen_assembly_hi, assembly_tet3=gen_assembly_tet3, mass=gen_mass,
                 laplacian=gen_laplacian,
                 explicit=gen_explicit, explicit_rules=gen_explicit_rules)
     for w in which:

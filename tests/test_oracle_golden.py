@@ -152,6 +152,25 @@ def test_laplacian_vs_reference_python_path(golden):
         assert abs(K1 - K).max() <= 1e-13 * abs(Kref).max()
 
 
+def test_consistent_and_lumped_mass_vs_reference_python_path(golden):
+    """a18: the consistent mass of the reference's Python path (Assemble, analysis_type="dynamic", optimise=False; fixtures of
+    tests/golden/make_golden.py gen_mass) pins __TotalConstantMassIntegrand__'s consistent branch, incl. the zero rows of the
+    potential dof (nvar = 4) and cubic tetrahedra; the lumped vector is its row sum (_MassIntegrand_.h:352-366)."""
+    g = golden.mass
+    for key in [str(s) for s in g["mass_cases"]]:
+        P, E = g[key + "_points"], g[key + "_elements"]
+        nvar, rho = int(g[key + "_nvar"]), float(g[key + "_rho"])
+        n = nvar * P.shape[0]
+        Mref = csr_matrix((g[key + "_M_data"], g[key + "_M_indices"], g[key + "_M_indptr"]), shape=(n, n))
+        I, J, V = orc.assemble_mass(P, E, g[key + "_Bases"], g[key + "_Jm"], g[key + "_AllGauss"], nvar, rho, "consistent")
+        M = csr_matrix((V, (I, J)), shape=(n, n))
+        assert abs(M - Mref).max() <= 1e-13 * abs(Mref).max(), key
+        Ml = orc.assemble_mass(P, E, g[key + "_Bases"], g[key + "_Jm"], g[key + "_AllGauss"], nvar, rho, "lumped")
+        assert np.abs(Ml - np.asarray(Mref.sum(axis=1)).ravel()).max() <= 1e-13 * np.abs(Ml).max(), key
+        if nvar > P.shape[1]:
+            assert np.abs(Ml[P.shape[1]::nvar]).max() == 0.0, key
+
+
 def test_explicit_force_mass_and_trajectory_vs_reference_integrator(golden):
     g = golden.explicit
     pts, els, Jm, AG, Bases = g["exp_points"], g["exp_elements"], g["exp_Jm"], g["exp_AllGauss"], g["exp_Bases"]
