@@ -193,12 +193,15 @@ def test_explicit_force_mass_and_trajectory_vs_reference_integrator(golden):
         assert np.abs(U - ref[:, :, inc]).max() <= 1e-11 * np.abs(ref).max(), inc
 
 
-def test_explicit_equals_implicit_traction():
-    """a12 and a5 integrate the same B^T sigma: T from the matrix-free path equals T of the implicit path."""
-    import os
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_assembly.npz"))
-    for key, nvar, form in (("asm_hex2_n2_MooneyRivlin", 3, 0), ("asm_quad2_n3_NeoHookean", 2, 0), ("asm_hex2_n1_IsotropicElectroMechanics_108", 4, 1),
-                            ("asm_tri2_n2_IsotropicElectroMechanics_101", 3, 1)):
+def test_explicit_equals_implicit_traction(golden):
+    """a12 and a5 integrate the same B^T sigma: T from the matrix-free path equals the reference's T of the implicit path, for every
+    fixture whose geometry is updated (all but the linear ones): 2-D and 3-D, p = 1..3, mechanics and electro-mechanics."""
+    cases = [(f, k) for f, k in _asm_cases() if "LinearElastic" not in k]
+    assert len(cases) >= 20
+    for fixture, key in cases:
+        g = getattr(golden, fixture)
+        form = 1 if key.split("_", 3)[3] in ELEC else 0
+        nvar = g[key + "_points"].shape[1] + form
         c = _case(g, key)
         num = orc.MATERIAL_NUMBERS[key.split("_", 3)[3]]
         T = orc.assemble_explicit(c["points"], c["elements"], c["Eulerx"], c["Eulerp"], c["Jm"], c["AllGauss"], nvar, c["prm"], num, form)
